@@ -1,0 +1,419 @@
+// power_kernels.cu — rx_power hot path on sm_100a: scanner()'s per-hop body
+// (src/rtl_power.c:709-771) batched over (hop, pass) work items.
+//
+//   copy (:715-720) -> remove_dc x2 (:609-624, :744-745) -> per N-point block:
+//   window multiply with int16 wrap (:749-758) -> fix_fft (:264-320) -> real_conj accumulate
+//   (:664-668, :760-768);  rms_power (:403-429) when bin_e == 0.
+//
+// One CTA owns a hop and a slice of that hop's passes.  Each hop buffer (buf_len int16, 32 KiB in
+// the BASELINE configs) is staged HBM -> shared memory by ONE bulk-TMA copy (cp.async.bulk +
+// mbarrier), transformed in place in shared memory, and only the |X|^2 sums leave the SM: they are
+// accumulated in registers across the CTA's passes and flushed with one 64-bit atomic per bin per
+// CTA (integer sums / max are order independent, so the result is bit-exact).  Algorithmic HBM
+// traffic: 4 B per used complex sample.  The FFT is the reference's radix-2 DIT with its per-stage
+// halving and FIX_MPY rounding reproduced exactly — this is integer-issue bound, not HBM bound
+// (DESIGN.md "rx_power kernel"); tensor cores do not apply (per-stage rounding).
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include "common.cuh"
+
+namespace rxb {
+
+struct PowArgs {
+	const int16_t *bufs;     // [n_pass][n_hops_call][buf_len]
+	long long *avg;          // [n_hops_total][N]
+	const int16_t *sine;     // 3N/4
+	const int16_t *window;   // N (low 16 bits of window_coefs; exact, see below)
+	int n_pass, n_hops_call, hop_begin;
+	int buf_len, bin_e, slices, peak_hold;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk TMA: contiguous global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ int plo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+__device__ __forceinline__ int phi(uint32_t w) { return (int)(int16_t)(w >> 16); }
+__device__ __forceinline__ uint32_t ppack(int re, int im) { return ((uint32_t)re & 0xffffu) | ((uint32_t)im << 16); }
+
+// FIX_MPY (src/rtl_power.c:256-262): c = (a*b)>>14; (c>>1)+(c&1)  ==  (a*b + 2^14) >> 15.
+// The int16 truncation of its result and of tr/ti is deferred to the final pack: everything in
+// between is addition modulo 2^16.
+__device__ __forceinline__ int q15(int a, int b) { return (a * b + 16384) >> 15; }
+
+__device__ __forceinline__ long long block_sum(long long v, long long *red, int tid, int nthreads)
+{
+	for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); }
+	__syncthreads();
+	if ((tid & 31) == 0) { red[tid >> 5] = v; }
+	__syncthreads();
+	long long t = 0;
+	for (int w = 0; w < (nthreads >> 5); w++) { t += red[w]; }
+	return t;
+}
+
+// NB = bins accumulated in registers per thread (N / blockDim); NB == 0: N too large, accumulate
+// straight into global memory after every block.
+template <int NB>
+__global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int tid = threadIdx.x, T = blockDim.x;
+	const int N = 1 << a.bin_e;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+	long long *red = reinterpret_cast<long long *>(smem_raw + 16);            // 32 x 8 B
+	uint32_t *buf = reinterpret_cast<uint32_t *>(smem_raw + 16 + 256);        // buf_len/2 words
+	int16_t *sine = reinterpret_cast<int16_t *>(buf + a.buf_len / 2);         // 3N/4
+	int16_t *win = sine + ((N * 3 / 4 + 7) & ~7);                             // N
+	const int hop_local = blockIdx.x / a.slices;
+	const int slice = blockIdx.x % a.slices;
+	const int hop = a.hop_begin + hop_local;
+
+	for (int i = tid; i < N * 3 / 4; i += T) { sine[i] = a.sine[i]; }
+	for (int i = tid; i < N; i += T) { win[i] = a.window[i]; }
+	if (tid == 0) { mbar_init(bar, 1); }
+	__syncthreads();
+
+	long long acc[NB > 0 ? NB : 1];
+#pragma unroll
+	for (int b = 0; b < (NB > 0 ? NB : 1); b++) { acc[b] = 0; }
+
+	const int used = a.buf_len;                 // downsample == 1 on this path
+	const int nblk = used / (2 * N);
+	uint32_t parity = 0;
+	for (int pass = slice; pass < a.n_pass; pass += a.slices) {
+		const int16_t *src = a.bufs + ((size_t)pass * a.n_hops_call + hop_local) * (size_t)a.buf_len;
+		if (tid == 0) {
+			fence_async_smem();                  // earlier generic-proxy writes to buf are ordered before the TMA write
+			mbar_expect_tx(bar, (uint32_t)a.buf_len * 2u);
+			bulk_load(buf, src, (uint32_t)a.buf_len * 2u, bar);
+		}
+		mbar_wait(bar, parity);
+		parity ^= 1u;
+		// remove_dc: sum of one component divided by the int16 span (src/rtl_power.c:609-624)
+		long long si = 0, sq = 0;
+		for (int i = tid; i < used / 2; i += T) { uint32_t w = buf[i]; si += plo(w); sq += phi(w); }
+		si = block_sum(si, red, tid, T);
+		sq = block_sum(sq, red, tid, T);
+		const int ave_i = (int)(int16_t)(si / (long long)used);
+		const int ave_q = (int)(int16_t)(sq / (long long)(used - 1));
+		for (int blk = 0; blk < nblk; blk++) {
+			uint32_t *x = buf + (size_t)blk * N;
+			// window (x - ave) * w with int16 wrap (:749-758) fused with the bit-reversal swap (:275-290)
+			for (int i = tid; i < N; i += T) {
+				int r = (int)(__brev((unsigned)i) >> (32 - a.bin_e));
+				if (i < r) {
+					uint32_t u = x[i], v = x[r];
+					int wi_ = win[i], wr_ = win[r];
+					x[r] = ppack((plo(u) - ave_i) * wi_, (phi(u) - ave_q) * wi_);
+					x[i] = ppack((plo(v) - ave_i) * wr_, (phi(v) - ave_q) * wr_);
+				} else if (i == r) {
+					uint32_t u = x[i];
+					int wi_ = win[i];
+					x[i] = ppack((plo(u) - ave_i) * wi_, (phi(u) - ave_q) * wi_);
+				}
+			}
+			__syncthreads();
+			// radix-2 DIT stages, every stage halves (:291-318)
+			for (int s = 0; s < a.bin_e; s++) {
+				const int l = 1 << s;
+				const int k = a.bin_e - 1 - s;
+				for (int t = tid; t < N / 2; t += T) {
+					int m = t & (l - 1);
+					int i = ((t >> s) << (s + 1)) + m;
+					int j = i + l;
+					int jt = m << k;
+					int wr = (int)sine[jt + N / 4] >> 1;
+					int wi = (-(int)sine[jt]) >> 1;
+					uint32_t u = x[i], v = x[j];
+					int vr = plo(v), vi = phi(v);
+					int tr = q15(wr, vr) - q15(wi, vi);
+					int ti = q15(wr, vi) + q15(wi, vr);
+					int qr = plo(u) >> 1, qi = phi(u) >> 1;
+					x[j] = ppack(qr - tr, qi - ti);
+					x[i] = ppack(qr + tr, qi + ti);
+				}
+				__syncthreads();
+			}
+			// real_conj accumulate (:664-668, :760-768)
+			if (NB > 0) {
+#pragma unroll
+				for (int b = 0; b < (NB > 0 ? NB : 1); b++) {
+					int j = tid + b * T;
+					if (j < N) {
+						uint32_t w = x[j];
+						int re = plo(w), im = phi(w);
+						long long pw = (long long)(re * re) + (long long)(im * im);
+						if (a.peak_hold) { acc[b] = pw > acc[b] ? pw : acc[b]; } else { acc[b] += pw; }
+					}
+				}
+			} else {
+				long long *row = a.avg + (size_t)hop * N;
+				for (int j = tid; j < N; j += T) {
+					uint32_t w = x[j];
+					int re = plo(w), im = phi(w);
+					long long pw = (long long)(re * re) + (long long)(im * im);
+					if (a.peak_hold) { atomicMax(row + j, pw); }
+					else { atomicAdd(reinterpret_cast<unsigned long long *>(row + j), (unsigned long long)pw); }
+				}
+			}
+		}
+		__syncthreads();       // everyone done with buf before the next TMA overwrites it
+	}
+	if (NB > 0) {
+		long long *row = a.avg + (size_t)hop * N;
+#pragma unroll
+		for (int b = 0; b < (NB > 0 ? NB : 1); b++) {
+			int j = tid + b * T;
+			if (j < N) {
+				if (a.peak_hold) { atomicMax(row + j, acc[b]); }
+				else { atomicAdd(reinterpret_cast<unsigned long long *>(row + j), (unsigned long long)acc[b]); }
+			}
+		}
+	}
+}
+
+// rms_power (src/rtl_power.c:403-429): one value per hop buffer.
+__global__ void __launch_bounds__(256) power_rms_kernel(const PowArgs a)
+{
+	__shared__ long long red[32];
+	const int tid = threadIdx.x, T = blockDim.x;
+	const int hop_local = blockIdx.x / a.slices;
+	const int slice = blockIdx.x % a.slices;
+	const int hop = a.hop_begin + hop_local;
+	long long acc = 0;
+	for (int pass = slice; pass < a.n_pass; pass += a.slices) {
+		const int16_t *src = a.bufs + ((size_t)pass * a.n_hops_call + hop_local) * (size_t)a.buf_len;
+		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+		long long t = 0, p = 0;
+		for (int i = tid; i < a.buf_len / 8; i += T) {
+			uint4 v = __ldg(src4 + i);
+			uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				int s0 = plo(ws[q]), s1 = phi(ws[q]);
+				t += s0 + s1;
+				p += (long long)(s0 * s0) + (long long)(s1 * s1);
+			}
+		}
+		t = block_sum(t, red, tid, T);
+		p = block_sum(p, red, tid, T);
+		if (tid == 0) {
+			// dc = t/buf_len; err = t*2*dc - dc*dc*buf_len; p -= round(err): same operation order as the
+			// reference, no fused multiply-add
+			double dc = __ddiv_rn((double)t, (double)a.buf_len);
+			double e1 = __dmul_rn((double)(t * 2), dc);
+			double e2 = __dmul_rn(__dmul_rn(dc, dc), (double)a.buf_len);
+			double err = __dsub_rn(e1, e2);
+			p -= (long long)round(err);
+			if (a.peak_hold) { acc = p > acc ? p : acc; } else { acc += p; }
+		}
+	}
+	if (tid == 0) {
+		if (a.peak_hold) { atomicMax(a.avg + hop, acc); }
+		else { atomicAdd(reinterpret_cast<unsigned long long *>(a.avg + hop), (unsigned long long)acc); }
+	}
+}
+
+}  // namespace rxb
+
+using namespace rxb;
+
+struct rxb200_power {
+	rxb200_power_params p;
+	int device;
+	cudaStream_t stream;
+	long long *d_avg;          // [n_hops][N]
+	int16_t *d_sine, *d_window;
+	int16_t *d_in; size_t d_in_cap;
+	std::vector<int> samples;  // tunes[i].samples mirror (deterministic, kept on the host)
+	int launches;
+	int n_sm;
+};
+
+static int power_validate(const rxb200_power_params *p)
+{
+	if (p->n_hops < 1 || p->bin_e < 0 || p->bin_e > 21 || p->buf_len < 16 || (p->buf_len % 8) != 0) {
+		set_error("bad rx_power parameters"); return RXB200_EINVAL;
+	}
+	if (p->bin_e > 0) {
+		if (p->downsample != 1 || p->downsample_passes != 0) {
+			set_error("rx_power small-span decimators (downsample %d, passes %d) not implemented yet", p->downsample, p->downsample_passes);
+			return RXB200_EUNSUPPORTED;
+		}
+		long long need = 16 + 256 + (long long)p->buf_len * 2 + (((3LL << p->bin_e) / 4 + 7) & ~7LL) * 2 + (2LL << p->bin_e);
+		if (need > 227 * 1024 || (2 << p->bin_e) > p->buf_len) {
+			set_error("bin_e %d with buf_len %d does not fit shared memory", p->bin_e, p->buf_len);
+			return RXB200_EUNSUPPORTED;
+		}
+	}
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_power_create(const rxb200_power_params *params, const int *window_coefs,
+                                   const int16_t *sinewave, int device, rxb200_power **out)
+{
+	if (!params || !out || (params->bin_e > 0 && !window_coefs)) { set_error("null argument"); return RXB200_EINVAL; }
+	*out = nullptr;
+	int rc = power_validate(params);
+	if (rc != RXB200_OK) { return rc; }
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device: librxb200 has no CPU fallback"); return RXB200_ENODEV; }
+	if (device < 0 || device >= ndev) { set_error("device %d out of range (%d)", device, ndev); return RXB200_ENODEV; }
+	RXB_CUDA(cudaSetDevice(device));
+	rxb200_power *h = new (std::nothrow) rxb200_power();
+	if (!h) { return RXB200_ENOMEM; }
+	h->p = *params; h->device = device; h->d_avg = nullptr; h->d_sine = nullptr; h->d_window = nullptr;
+	h->d_in = nullptr; h->d_in_cap = 0; h->launches = 0;
+	h->samples.assign(params->n_hops, 0);
+	cudaDeviceProp prop;
+	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
+	h->n_sm = prop.multiProcessorCount;
+	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	const size_t N = (size_t)1 << params->bin_e;
+	RXB_CUDA(cudaMalloc(&h->d_avg, (size_t)params->n_hops * N * sizeof(long long)));
+	RXB_CUDA(cudaMemset(h->d_avg, 0, (size_t)params->n_hops * N * sizeof(long long)));
+	if (params->bin_e > 0) {
+		std::vector<int16_t> sine(N * 3 / 4 + 8), win(N);
+		if (sinewave) { memcpy(sine.data(), sinewave, (N * 3 / 4) * sizeof(int16_t)); }
+		else { rxb200_sine_table(params->bin_e, sine.data()); }
+		// (int16)(x * w) depends only on w modulo 2^16, so the table is kept as int16
+		for (size_t i = 0; i < N; i++) { win[i] = (int16_t)window_coefs[i]; }
+		RXB_CUDA(cudaMalloc(&h->d_sine, sine.size() * sizeof(int16_t)));
+		RXB_CUDA(cudaMalloc(&h->d_window, win.size() * sizeof(int16_t)));
+		RXB_CUDA(cudaMemcpy(h->d_sine, sine.data(), sine.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+		RXB_CUDA(cudaMemcpy(h->d_window, win.data(), win.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+	}
+	*out = h;
+	return RXB200_OK;
+}
+
+extern "C" void rxb200_power_destroy(rxb200_power *h)
+{
+	if (!h) { return; }
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	cudaFree(h->d_avg); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in);
+	cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+template <int NB>
+static cudaError_t launch_fft(const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
+{
+	cudaError_t e = cudaFuncSetAttribute(power_fft_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) { return e; }
+	power_fft_kernel<NB><<<blocks, 256, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_hop_bufs, int n_pass,
+                                              int hop_begin, int hop_end, int sync)
+{
+	if (!h || !d_hop_bufs) { set_error("null argument"); return RXB200_EINVAL; }
+	if (n_pass < 0 || hop_begin < 0 || hop_end > h->p.n_hops || hop_begin >= hop_end) { set_error("bad hop range"); return RXB200_EINVAL; }
+	if (((uintptr_t)d_hop_bufs & 15u) != 0) { set_error("hop buffers must be 16-byte aligned"); return RXB200_EINVAL; }
+	if (n_pass == 0) { return RXB200_OK; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	const int nh = hop_end - hop_begin;
+	PowArgs a;
+	a.bufs = d_hop_bufs; a.avg = h->d_avg; a.sine = h->d_sine; a.window = h->d_window;
+	a.n_pass = n_pass; a.n_hops_call = nh; a.hop_begin = hop_begin; a.buf_len = h->p.buf_len;
+	a.bin_e = h->p.bin_e; a.peak_hold = h->p.peak_hold;
+	// enough CTAs for ~4 per SM, never more slices than passes
+	int slices = (h->n_sm * 4 + nh - 1) / nh;
+	if (slices > n_pass) { slices = n_pass; }
+	if (slices < 1) { slices = 1; }
+	a.slices = slices;
+	const int blocks = nh * slices;
+	if (h->p.bin_e == 0) {
+		power_rms_kernel<<<blocks, 256, 0, h->stream>>>(a);
+		RXB_CUDA(cudaGetLastError());
+		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass; }                      // :428
+	} else {
+		const int N = 1 << h->p.bin_e;
+		size_t smem = 16 + 256 + (size_t)h->p.buf_len * 2 + (size_t)((N * 3 / 4 + 7) & ~7) * 2 + (size_t)N * 2;
+		cudaError_t e;
+		const int nb = N / 256;
+		if (nb <= 1) { e = launch_fft<1>(a, blocks, smem, h->stream); }
+		else if (nb == 2) { e = launch_fft<2>(a, blocks, smem, h->stream); }
+		else if (nb == 4) { e = launch_fft<4>(a, blocks, smem, h->stream); }
+		else if (nb == 8) { e = launch_fft<8>(a, blocks, smem, h->stream); }
+		else if (nb == 16) { e = launch_fft<16>(a, blocks, smem, h->stream); }
+		else { e = launch_fft<0>(a, blocks, smem, h->stream); }
+		if (e != cudaSuccess) { set_error("power_fft_kernel launch: %s", cudaGetErrorString(e)); return RXB200_ECUDA; }
+		const int per_buf = (h->p.buf_len / h->p.downsample) / (2 * N);
+		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass * per_buf * h->p.downsample; }   // :769
+	}
+	h->launches = 1;
+	if (sync) { RXB_CUDA(cudaStreamSynchronize(h->stream)); }
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_power_accumulate(rxb200_power *h, const int16_t *hop_bufs, int n_pass, int hop_begin, int hop_end)
+{
+	if (!h || !hop_bufs) { set_error("null argument"); return RXB200_EINVAL; }
+	if (n_pass < 0 || hop_begin < 0 || hop_end > h->p.n_hops || hop_begin >= hop_end) { set_error("bad hop range"); return RXB200_EINVAL; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	size_t elems = (size_t)n_pass * (size_t)(hop_end - hop_begin) * (size_t)h->p.buf_len;
+	if (elems == 0) { return RXB200_OK; }
+	if (elems > h->d_in_cap) {
+		cudaFree(h->d_in); h->d_in = nullptr; h->d_in_cap = 0;
+		RXB_CUDA(cudaMalloc(&h->d_in, elems * sizeof(int16_t)));
+		h->d_in_cap = elems;
+	}
+	RXB_CUDA(cudaMemcpyAsync(h->d_in, hop_bufs, elems * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+	return rxb200_power_accumulate_device(h, h->d_in, n_pass, hop_begin, hop_end, 1);
+}
+
+extern "C" int rxb200_power_read(rxb200_power *h, int64_t *avg, int *samples)
+{
+	if (!h) { return RXB200_EINVAL; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	if (avg) {
+		const size_t N = (size_t)1 << h->p.bin_e;
+		RXB_CUDA(cudaMemcpyAsync(avg, h->d_avg, (size_t)h->p.n_hops * N * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+	}
+	RXB_CUDA(cudaStreamSynchronize(h->stream));
+	if (samples) { memcpy(samples, h->samples.data(), h->samples.size() * sizeof(int)); }
+	return RXB200_OK;
+}
+
+extern "C" int64_t *rxb200_power_device_avg(rxb200_power *h) { return h ? reinterpret_cast<int64_t *>(h->d_avg) : nullptr; }
+
+extern "C" int rxb200_power_reset(rxb200_power *h)
+{
+	if (!h) { return RXB200_EINVAL; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	const size_t N = (size_t)1 << h->p.bin_e;
+	RXB_CUDA(cudaMemsetAsync(h->d_avg, 0, (size_t)h->p.n_hops * N * sizeof(long long), h->stream));
+	for (size_t i = 0; i < h->samples.size(); i++) { h->samples[i] = 0; }
+	return RXB200_OK;
+}
+
+extern "C" void *rxb200_power_stream(rxb200_power *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int rxb200_power_last_launches(rxb200_power *h) { return h ? h->launches : 0; }

@@ -2,6 +2,8 @@
 
 The reference ships no tests or golden vectors, so the reference code itself,
 executed, is the pin.  These tests need oracle/_ref (built here from /root/reference)."""
+import dataclasses
+
 import numpy as np
 import pytest
 
@@ -48,7 +50,7 @@ def test_derivation_matches_optimal_settings(ref_fm):
     for kw in combos:
         want, cap_rate, cap_off = ref_fm.derive(**kw)
         got = fm.derive_params(**kw)
-        assert got.params == want, (kw, got.params, want)
+        assert dataclasses.asdict(got.params) == dataclasses.asdict(want), (kw, got.params, want)
         assert got.capture_rate == cap_rate and got.capture_freq_offset == cap_off, kw
 
 
