@@ -1,0 +1,90 @@
+"""rx_power parity: CUDA path through the C-ABI vs the port oracle and the golden vectors (int64
+accumulators must be bit-exact)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from cases import power_cases, power_input
+from rx_tools_b200 import _lib, power
+from rx_tools_b200.synth import digest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PW_GOLD = json.load(open(os.path.join(G, "power_golden.json")))
+
+
+def _oracle_params(plan):
+    return oracle.PowerParams(bin_e=plan.bin_e, buf_len=plan.buf_len, downsample=plan.downsample,
+                              downsample_passes=plan.downsample_passes, comp_fir_size=plan.comp_fir_size,
+                              boxcar=plan.boxcar, peak_hold=plan.peak_hold)
+
+
+@pytest.mark.parametrize("case", power_cases(), ids=lambda c: c.name)
+def test_power_matches_oracle_and_golden(case, port):
+    plan = power.plan_range(case.freq_arg, case.crop, case.boxcar, case.comp_fir_size, case.peak_hold)
+    n = 1 << plan.bin_e
+    win = power.window_table(case.window, n)
+    x = power_input(case, plan.n_hops, plan.buf_len)
+    want_avg, want_smp = port.power_scan(_oracle_params(plan), win, x, case.n_pass, plan.n_hops)
+    try:
+        sc = power.PowerScanner(plan, win)
+    except _lib.Rxb200Error as e:
+        assert e.code == _lib.EUNSUPPORTED
+        pytest.xfail("small-span decimators / huge FFT not implemented yet (SURVEY §8f row 3)")
+    sc.scanner(x, case.n_pass)
+    avg, smp = sc.read()
+    assert np.array_equal(smp, want_smp)
+    bad = np.argwhere(avg != want_avg)
+    assert bad.size == 0, (bad[:4], avg[tuple(bad[0])], want_avg[tuple(bad[0])])
+    assert digest(avg) == PW_GOLD[case.name]["avg_sha256"]
+    # second batch accumulates on top (or keeps the max); reset zeroes like csv_dbm
+    sc.scanner(x, case.n_pass)
+    avg2, smp2 = sc.read()
+    assert np.array_equal(avg2, want_avg if case.peak_hold else 2 * want_avg)
+    assert np.array_equal(smp2, 2 * want_smp)
+    sc.reset()
+    z, zs = sc.read()
+    assert not z.any() and not zs.any()
+    sc.close()
+
+
+def test_hop_subranges_equal_full_sweep(port):
+    """Sharding by hop (what each GPU rank does) gives the same rows as the full sweep."""
+    case = next(c for c in power_cases() if c.name == "cfg4_small")
+    plan = power.plan_range(case.freq_arg, case.crop)
+    win = power.window_table(case.window, 1 << plan.bin_e)
+    x = power_input(case, plan.n_hops, plan.buf_len)
+    want, _ = port.power_scan(_oracle_params(plan), win, x, case.n_pass, plan.n_hops)
+    sc = power.PowerScanner(plan, win)
+    for a, b in [(0, 5), (5, 6), (6, plan.n_hops)]:
+        sc.scanner(np.ascontiguousarray(x[:, a:b]), case.n_pass, a, b)
+    avg, _ = sc.read()
+    assert np.array_equal(avg, want)
+    sc.close()
+
+
+def test_many_passes_one_hop(port):
+    """cfg3 shape: one hop, many passes split over many CTAs + atomics."""
+    plan = power.plan_range("100M:101M:1k")
+    win = power.window_table("hann-poisson", 1024)
+    rng = np.random.default_rng(3)
+    x = rng.integers(-120, 121, size=(700, 1, plan.buf_len), dtype=np.int32).astype(np.int16)
+    want, ws = port.power_scan(_oracle_params(plan), win, x, 700, 1)
+    sc = power.PowerScanner(plan, win)
+    sc.scanner(x, 700)
+    avg, smp = sc.read()
+    assert np.array_equal(avg, want) and np.array_equal(smp, ws)
+    sc.close()
+
+
+def test_literal_vectors():
+    z = np.load(os.path.join(G, "literal_vectors.npz"))
+    plan = power.plan_range("100M:101M:1k")
+    sc = power.PowerScanner(plan, "hamming")
+    sc.scanner(z["pw_in"], 2)
+    avg, smp = sc.read()
+    assert np.array_equal(avg, z["pw_avg"]) and np.array_equal(smp, z["pw_samples"])
+    sc.close()
