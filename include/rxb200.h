@@ -158,6 +158,9 @@ int rxb200_fm_last_stats(rxb200_fm *h, rxb200_fm_stats *out);
 /* Tuning knobs (0 keeps the automatic choice): segment length in complex samples, de-emphasis
  * warm-up in decimated samples. */
 int rxb200_fm_tune(rxb200_fm *h, int segment_len, int deemph_warmup);
+/* Device time (CUDA events on the handle's stream) of the fused kernel alone in the last process
+ * call, in milliseconds.  Synchronises the stream. */
+int rxb200_fm_kernel_ms(rxb200_fm *h, float *ms);
 
 /* ======================================================================== rx_power
  * Replaces scanner()'s per-hop body (src/rtl_power.c:709-771): copy, boxcar | downsample_iq x P +
@@ -225,6 +228,8 @@ int64_t *rxb200_power_device_avg(rxb200_power *h);
 int rxb200_power_reset(rxb200_power *h);
 void *rxb200_power_stream(rxb200_power *h);
 int rxb200_power_last_launches(rxb200_power *h);
+/* Device time of the batched kernel alone in the last accumulate call (ms); synchronises. */
+int rxb200_power_kernel_ms(rxb200_power *h, float *ms);
 
 /* csv_dbm() (src/rtl_power.c:774-817) for one hop row on the host: formats
  * "Hz low, Hz high, Hz step, samples, dB, dB, ...\n" into dst (the caller prints the date/time

@@ -524,6 +524,7 @@ struct rxb200_fm {
 	int tune_seg, tune_warm;
 	rxb200_fm_stats stats;
 	fm_kernel_fn main_k, fix_k;
+	cudaEvent_t ev0, ev1;
 };
 
 static int fm_validate(const rxb200_fm_params *p)
@@ -590,6 +591,8 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	h->state_words = fm_state_words(params->downsample_passes);
 	pick_kernels(params->downsample_passes, &h->main_k, &h->fix_k);
 	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	RXB_CUDA(cudaEventCreate(&h->ev0));
+	RXB_CUDA(cudaEventCreate(&h->ev1));
 	size_t cbytes = (size_t)n_channels * h->state_words * sizeof(uint32_t);
 	RXB_CUDA(cudaMalloc(&h->d_carry[0], cbytes));
 	RXB_CUDA(cudaMalloc(&h->d_carry[1], cbytes));
@@ -629,8 +632,18 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 	cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_seg_state); cudaFree(h->d_seg_flags);
 	cudaFree(h->d_fix_count); cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
+	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
+}
+
+extern "C" int rxb200_fm_kernel_ms(rxb200_fm *h, float *ms)
+{
+	if (!h || !ms) { return RXB200_EINVAL; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	RXB_CUDA(cudaEventSynchronize(h->ev1));
+	RXB_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+	return RXB200_OK;
 }
 
 // closed-form per-chunk result_len; advances the host mirrors when commit is set
@@ -733,8 +746,10 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	k.seg_state = h->d_seg_state; k.seg_flags = h->d_seg_flags; k.fix_count = h->d_fix_count;
 	RXB_CUDA(cudaMemsetAsync(h->d_fix_count, 0, sizeof(int), h->stream));
 	unsigned blocks = (unsigned)((total_seg + 127) / 128);
+	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
 	h->main_k<<<blocks, 128, 0, h->stream>>>(h->dev, k);
 	RXB_CUDA(cudaGetLastError());
+	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
 	int launches = 1;
 	if (nseg > 1) {
 		h->fix_k<<<blocks, 128, 0, h->stream>>>(h->dev, k);

@@ -253,6 +253,7 @@ struct rxb200_power {
 	std::vector<int> samples;  // tunes[i].samples mirror (deterministic, kept on the host)
 	int launches;
 	int n_sm;
+	cudaEvent_t ev0, ev1;
 };
 
 static int power_validate(const rxb200_power_params *p)
@@ -294,6 +295,8 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
 	h->n_sm = prop.multiProcessorCount;
 	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	RXB_CUDA(cudaEventCreate(&h->ev0));
+	RXB_CUDA(cudaEventCreate(&h->ev1));
 	const size_t N = (size_t)1 << params->bin_e;
 	RXB_CUDA(cudaMalloc(&h->d_avg, (size_t)params->n_hops * N * sizeof(long long)));
 	RXB_CUDA(cudaMemset(h->d_avg, 0, (size_t)params->n_hops * N * sizeof(long long)));
@@ -318,8 +321,18 @@ extern "C" void rxb200_power_destroy(rxb200_power *h)
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_avg); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in);
+	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
+}
+
+extern "C" int rxb200_power_kernel_ms(rxb200_power *h, float *ms)
+{
+	if (!h || !ms) { return RXB200_EINVAL; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	RXB_CUDA(cudaEventSynchronize(h->ev1));
+	RXB_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+	return RXB200_OK;
 }
 
 template <int NB>
@@ -350,6 +363,7 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 	if (slices < 1) { slices = 1; }
 	a.slices = slices;
 	const int blocks = nh * slices;
+	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
 	if (h->p.bin_e == 0) {
 		power_rms_kernel<<<blocks, 256, 0, h->stream>>>(a);
 		RXB_CUDA(cudaGetLastError());
@@ -369,6 +383,7 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		const int per_buf = (h->p.buf_len / h->p.downsample) / (2 * N);
 		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass * per_buf * h->p.downsample; }   // :769
 	}
+	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
 	h->launches = 1;
 	if (sync) { RXB_CUDA(cudaStreamSynchronize(h->stream)); }
 	return RXB200_OK;

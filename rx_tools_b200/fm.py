@@ -125,6 +125,11 @@ class FmDemod:
     def stream(self) -> int:
         return int(_lib.lib().rxb200_fm_stream(self._h) or 0)
 
+    def kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(_lib.lib().rxb200_fm_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def stats(self) -> dict:
         s = _lib.FmStatsC()
         _lib.check(_lib.lib().rxb200_fm_last_stats(self._h, C.byref(s)))

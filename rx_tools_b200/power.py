@@ -119,6 +119,11 @@ class PowerScanner:
     def reset(self) -> None:
         _lib.check(_lib.lib().rxb200_power_reset(self._h))
 
+    def kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(_lib.lib().rxb200_power_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     @property
     def device_avg_ptr(self) -> int:
         return int(_lib.lib().rxb200_power_device_avg(self._h) or 0)

@@ -117,7 +117,7 @@ def test_scale_identity_on_gpu(port):
 
 def test_ragged_and_bad_shapes_fail_loudly():
     d = fm.FmDemod(fm.FmParams(downsample=8, downsample_passes=3, comp_fir_size=9, custom_atan=1, rate_out=300000))
-    x = np.zeros(2 * 1000, dtype=np.int16)          # not a multiple of 16 int16
+    x = np.zeros(2 * 1001, dtype=np.int16)          # not a multiple of 16 int16
     with pytest.raises(_lib.Rxb200Error) as e:
         d.full_demod(x, 262144)
     assert e.value.code == _lib.EUNSUPPORTED
