@@ -1,21 +1,26 @@
-// fm_kernels.cu — rx_fm hot path on sm_100a: ONE fused kernel per stream batch covering
+// fm_kernels.cu — rx_fm hot path on sm_100a: ONE fused kernel per call covering
 //   CS16->8-bit-range scale (src/rtl_fm.c:846) -> rotate16_90 (:309) -> low_pass (:351) |
 //   fifth_order x P (:411) + generic_fir (:442) -> fm_demod (:584; std/fast/lut/ale) | am/usb/lsb/raw
 //   -> deemph_filter (:667) -> low_pass_real (:389)
 // with no intermediate buffer in HBM (algorithmic traffic: 4 B in + 2*rate_out2/rate_capture B out
 // per complex sample).
 //
-// Parallel decomposition (DESIGN.md "rx_fm kernel"): the stream of every channel is cut into
-// segments of S complex samples; one THREAD owns one segment and runs the reference's per-sample
-// state machine over it with all carry state in registers.  To know the state at its segment
-// start without waiting for its left neighbour it first replays `warm` samples before the segment:
-//   * decimators / FIRs / discriminator have finite memory, so the replay makes them exact;
-//   * deemph_filter is a rounding (non-linear) IIR: the replay runs it from BOTH extreme states
-//     (-32768 and +32767).  The step map is monotone in the state, so the true state is bracketed,
-//     and once the two trajectories meet the state is exact (SURVEY.md §7 hard part 2).
-// Segments whose brackets have not met at the segment start (quiet input: the IIR has a dead
-// zone) are flagged and recomputed serially from their neighbour's exact end state by
-// fm_fixup_kernel, so the result is bit-exact for every input.
+// Decomposition (DESIGN.md "rx_fm kernel"):
+//   * A CTA (256 threads) owns a contiguous stretch of one channel's stream.  FRONT END: every
+//     thread runs scale/rotate/decimate/FIR/discriminator over its own Sf-sample segment, all state
+//     in registers, after replaying `halo` samples so the finite-memory filters are exact; the
+//     demodulated PCM (one int16 per decimated sample) goes to shared memory only.
+//   * BACK END: warp 0 runs the serial stages (deemph_filter, low_pass_real) over the CTA's PCM,
+//     one contiguous piece per lane.  deemph_filter is a rounding (non-linear) IIR, so each lane
+//     replays W_dec PCM samples before its piece from BOTH extreme states (-32768 / +32767): the
+//     step map is monotone in the state, the true state is bracketed, and once the two
+//     trajectories meet it is exact (SURVEY.md §7 hard part 2).  Lanes whose bracket has not
+//     closed (quiet input: the IIR has a dead zone) are re-run from their left neighbour's exact
+//     end state, in-warp via shuffles and across CTAs via a published end state (CTAs take work
+//     tickets in order, so a CTA only ever waits for an older one).  The result is bit-exact for
+//     every input.
+//   * The halo/warm-up PCM a CTA needs from before its stretch is recomputed by `n_extra` of its
+//     own threads, so nothing but the CS16 stream is read from HBM and nothing but PCM written.
 // Per-chunk semantics (rotation phase restart, fifth_order dropping the last sample of a chunk,
 // first FM output of a chunk through atan2: SURVEY F7, F8) are reproduced literally: the chunk
 // length is a kernel argument.
@@ -28,11 +33,14 @@
 
 namespace rxb {
 
+#define FM_THREADS 256
+#define FM_MAX_PACKED 3          // fifth_order passes run as packed I/Q SWAR (bias keeps lanes unsigned)
+
 // ------------------------------------------------------------------------------ device config
 struct FmDev {
-	int mode, D, P, fir_on, atan_mode, out_scale, post_ds;
+	int mode, D, P, PL, fir_on, atan_mode, out_scale, post_ds;
 	int deemph, a, a_half, a_even;
-	unsigned a_magic; int a_K, a_use_magic;   // floor((n)/a) == umulhi(n, a_magic) for n < 2^19
+	unsigned a_magic; int a_K, a_use_magic;   // floor(n/a) == umulhi(n, a_magic) for the n range used
 	int resample, fast, slow, lpr_div;
 	int offset_tuning;
 	int fir[6];
@@ -46,45 +54,57 @@ struct FmCall {
 	long long out_stride;     // int16 per channel
 	int chunk;                // complex samples per chunk
 	int n_ch;
-	int S;                    // segment length (complex)
-	int warm;                 // replay length before a segment (complex)
-	int dec_exact;            // decimated samples after which the replayed front end is exact
-	int nseg;                 // segments per channel
+	int Sf;                   // front-end segment (complex samples per thread)
+	int halo;                 // samples replayed before a segment
+	int n_extra, n_own;       // thread slots: warm-up region / owned stretch
+	int n_cta;                // CTAs per channel
+	int W_dec;                // back-end replay length (decimated samples)
+	int pcm_cap;              // int16 entries of the shared PCM buffer
+	int direct_out;           // 1: no serial stage, the front end stores the output itself
 	int state_words;
 	const uint32_t *carry_in; // [n_ch][state_words]
 	uint32_t *carry_out;      // [n_ch][state_words]
-	uint32_t *seg_state;      // [n_ch*nseg][state_words]  end state of every segment
-	int *seg_flags;           // [n_ch*nseg]  bit0 start exact, bit1 end exact
-	int *fix_count;           // number of segments recomputed by the fix-up kernel
+	int *ticket;              // work counter
+	int *pub;                 // [n_ch*n_cta][4]  flag, avg, lpr_acc, -
+	int *fix_count;           // lanes that had to be re-run from a neighbour's state
 };
 
-enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG_LO, ST_AVG_HI, ST_LPR_ACC,
-       ST_LPR_PHASE, ST_DIRTY, ST_SQ_HITS, ST_ADC, ST_RDC_I, ST_RDC_Q, ST_RSV0, ST_RSV1, ST_HDR = 16 };
+enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC, ST_LPR_PHASE,
+       ST_SQ_HITS, ST_ADC, ST_RDC_I, ST_RDC_Q, ST_HDR = 16 };
 
-static inline int fm_state_words(int P) { return ST_HDR + 7 * P + 9; }
+static inline int fm_packed_levels(int P) { return P < FM_MAX_PACKED ? P : FM_MAX_PACKED; }
+static inline int fm_state_words(int P) { int pl = fm_packed_levels(P); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
 
 __device__ __forceinline__ uint32_t pack2(int i, int q) { return ((uint32_t)i & 0xffffu) | ((uint32_t)q << 16); }
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
-// ------------------------------------------------------------------------------ per-thread state
+// ------------------------------------------------------------------------------ front-end state
 template <int P>
-struct FmState {
+struct FrontState {
+	static constexpr int PL = P < FM_MAX_PACKED ? P : FM_MAX_PACKED;
+	static constexpr int PS = P - PL;
 	int box_i, box_q, box_n;
-	int wi[P > 0 ? P : 1][6], wq[P > 0 ? P : 1][6];   // fifth_order windows (a..f) per pass
-	int pi[P > 0 ? P : 1], pq[P > 0 ? P : 1];         // odd-indexed sample waiting for its pair
-	int di[9], dq[9];                                 // generic_fir history
+	// packed passes: the last six samples the pass has seen (oldest first), I in the low and Q in
+	// the high half-word, each biased by 128<<level so both lanes stay unsigned
+	uint32_t h[PL > 0 ? PL : 1][6];
+	// scalar passes (level >= 3): the reference's window a..f plus the odd sample waiting for its pair
+	int wi[PS > 0 ? PS : 1][6], wq[PS > 0 ? PS : 1][6], pi[PS > 0 ? PS : 1], pq[PS > 0 ? PS : 1];
+	int di[9], dq[9];          // generic_fir history
 	int pre_i, pre_q;
-	int lo, hi, dirty;
-	int lpr_acc, lpr_phase;
 };
 
 template <int P>
-__device__ __forceinline__ void state_zero(FmState<P> &s)
+__device__ __forceinline__ void front_zero(FrontState<P> &s)
 {
 	s.box_i = s.box_q = s.box_n = 0;
 #pragma unroll
-	for (int l = 0; l < (P > 0 ? P : 1); l++) {
+	for (int l = 0; l < FrontState<P>::PL; l++) {
+#pragma unroll
+		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l); }
+	}
+#pragma unroll
+	for (int l = 0; l < FrontState<P>::PS; l++) {
 #pragma unroll
 		for (int j = 0; j < 6; j++) { s.wi[l][j] = 0; s.wq[l][j] = 0; }
 		s.pi[l] = 0; s.pq[l] = 0;
@@ -92,55 +112,70 @@ __device__ __forceinline__ void state_zero(FmState<P> &s)
 #pragma unroll
 	for (int j = 0; j < 9; j++) { s.di[j] = 0; s.dq[j] = 0; }
 	s.pre_i = s.pre_q = 0;
-	s.lo = -32768; s.hi = 32767; s.dirty = 1;
-	s.lpr_acc = 0; s.lpr_phase = 0;
 }
 
 template <int P>
-__device__ __forceinline__ void state_load(FmState<P> &s, const uint32_t *g)
+__device__ __forceinline__ void front_load(FrontState<P> &s, const uint32_t *g)
 {
+	constexpr int PL = FrontState<P>::PL, PS = FrontState<P>::PS;
 	s.box_i = (int)g[ST_BOX_I]; s.box_q = (int)g[ST_BOX_Q]; s.box_n = (int)g[ST_BOX_N];
 	s.pre_i = (int)g[ST_PRE_I]; s.pre_q = (int)g[ST_PRE_Q];
-	s.lo = (int)g[ST_AVG_LO]; s.hi = (int)g[ST_AVG_HI];
-	s.lpr_acc = (int)g[ST_LPR_ACC]; s.lpr_phase = (int)g[ST_LPR_PHASE];
-	s.dirty = (int)g[ST_DIRTY];
 #pragma unroll
-	for (int l = 0; l < P; l++) {
+	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { uint32_t w = g[ST_HDR + 7 * l + j]; s.wi[l][j] = lo16(w); s.wq[l][j] = hi16(w); }
-		uint32_t w = g[ST_HDR + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
+		for (int j = 0; j < 6; j++) { s.h[l][j] = g[ST_HDR + 6 * l + j]; }
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 7 * P + j]; s.di[j] = lo16(w); s.dq[j] = hi16(w); }
+	for (int l = 0; l < PS; l++) {
+#pragma unroll
+		for (int j = 0; j < 6; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * l + j]; s.wi[l][j] = lo16(w); s.wq[l][j] = hi16(w); }
+		uint32_t w = g[ST_HDR + 6 * PL + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
+	}
+#pragma unroll
+	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * PS + j]; s.di[j] = lo16(w); s.dq[j] = hi16(w); }
 }
 
 template <int P>
-__device__ __forceinline__ void state_store(const FmState<P> &s, uint32_t *g)
+__device__ __forceinline__ void front_store(const FrontState<P> &s, uint32_t *g)
 {
+	constexpr int PL = FrontState<P>::PL, PS = FrontState<P>::PS;
 	g[ST_BOX_I] = (uint32_t)s.box_i; g[ST_BOX_Q] = (uint32_t)s.box_q; g[ST_BOX_N] = (uint32_t)s.box_n;
 	g[ST_PRE_I] = (uint32_t)s.pre_i; g[ST_PRE_Q] = (uint32_t)s.pre_q;
-	g[ST_AVG_LO] = (uint32_t)s.lo; g[ST_AVG_HI] = (uint32_t)s.hi;
-	g[ST_LPR_ACC] = (uint32_t)s.lpr_acc; g[ST_LPR_PHASE] = (uint32_t)s.lpr_phase;
-	g[ST_DIRTY] = (uint32_t)s.dirty;
 #pragma unroll
-	for (int l = 0; l < P; l++) {
+	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { g[ST_HDR + 7 * l + j] = pack2(s.wi[l][j], s.wq[l][j]); }
-		g[ST_HDR + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
+		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * l + j] = s.h[l][j]; }
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { g[ST_HDR + 7 * P + j] = pack2(s.di[j], s.dq[j]); }
+	for (int l = 0; l < PS; l++) {
+#pragma unroll
+		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * PL + 7 * l + j] = pack2(s.wi[l][j], s.wq[l][j]); }
+		g[ST_HDR + 6 * PL + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
+	}
+#pragma unroll
+	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = pack2(s.di[j], s.dq[j]); }
 }
 
 // ------------------------------------------------------------------------------ stages
-// fifth_order cascade, one input sample at in-chunk index idx of pass L (src/rtl_fm.c:411-440,
-// :765-768).  A pass emits at even input indices: index 0 of a chunk slides the window by one
-// (a..e = hist[1..5], f = data[0]), every later even index by two (e = data[i-2], f = data[i]);
-// an odd-indexed sample waits in p* and is lost if the chunk ends on it.
-template <int L, int P>
-__device__ __forceinline__ bool cascade_push(FmState<P> &s, int xi, int xq, unsigned idx, int &oi, int &oq)
+// fifth_order tap set [1 5 10 10 5 1] >> 4 on two biased 16-bit lanes at once.  With inputs biased by
+// B (lane = v + B, |v| <= B) the lane sum is < 64 B <= 32768, so no carry crosses lanes, and
+// (sum + 32 B) >> 4 == (sum >> 4) + 2 B exactly: the output lanes are biased by 2 B.  The int16
+// store of the reference never wraps here because |v| <= 128 << level after the 8-bit-range scale.
+__device__ __forceinline__ uint32_t hb_tap(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f)
 {
-	if constexpr (L >= P) {
+	uint32_t s = a + f + (b + e) * 5u + (c + d) * 10u;
+	return (s >> 4) & 0x0FFF0FFFu;
+}
+
+// Scalar fifth_order pass for levels >= 3 (values may exceed the packed head-room; int16 wrap kept).
+// One input sample at in-chunk index idx of pass L (src/rtl_fm.c:411-440, :765-768): a pass emits at
+// even input indices; index 0 of a chunk slides the window by one (a..e = hist[1..5], f = data[0]),
+// every later even index by two; an odd-indexed sample waits and is lost if the chunk ends on it (F7).
+template <int L, int P>
+__device__ __forceinline__ bool scalar_push(FrontState<P> &s, int xi, int xq, unsigned idx, int &oi, int &oq)
+{
+	constexpr int PS = FrontState<P>::PS;
+	if constexpr (L >= PS) {
 		oi = xi; oq = xq;
 		return true;
 	} else {
@@ -156,7 +191,7 @@ __device__ __forceinline__ bool cascade_push(FmState<P> &s, int xi, int xq, unsi
 		s.wi[L][5] = xi; s.wq[L][5] = xq;
 		int yi = wrap16((s.wi[L][0] + (s.wi[L][1] + s.wi[L][4]) * 5 + (s.wi[L][2] + s.wi[L][3]) * 10 + s.wi[L][5]) >> 4);
 		int yq = wrap16((s.wq[L][0] + (s.wq[L][1] + s.wq[L][4]) * 5 + (s.wq[L][2] + s.wq[L][3]) * 10 + s.wq[L][5]) >> 4);
-		return cascade_push<L + 1, P>(s, yi, yq, idx >> 1, oi, oq);
+		return scalar_push<L + 1, P>(s, yi, yq, idx >> 1, oi, oq);
 	}
 }
 
@@ -217,9 +252,8 @@ __device__ __forceinline__ int disc_ale(int ar, int aj, int br, int bj)
 }
 
 // One deemph_filter step (src/rtl_fm.c:673-680): avg += trunc((d +- a/2)/a).
-//   d > 0 : trunc((d + h)/a)          = floor((d + h)/a)
-//   d <= 0: trunc((d - h)/a)          = floor((d - h + a - 1)/a)       (h = a/2)
-// i.e. floor((d + c)/a) with c = h for odd a, and c = h - (d <= 0) for even a.  With a bias of
+//   d > 0 : trunc((d + h)/a) = floor((d + h)/a);   d <= 0: trunc((d - h)/a) = floor((d - h + a - 1)/a)
+// i.e. floor((d + c)/a) with c = h for odd a and c = h - (d <= 0) for even a (h = a/2).  With a bias of
 // K*a the numerator is non-negative and the floor is one umulhi by a host-verified reciprocal.
 __device__ __forceinline__ int deemph_step(const FmDev &c, int avg, int x)
 {
@@ -232,254 +266,403 @@ __device__ __forceinline__ int deemph_step(const FmDev &c, int avg, int x)
 	return avg + ((d > 0) ? (d + c.a_half) / c.a : (d - c.a_half) / c.a);
 }
 
-// ------------------------------------------------------------------------------ segment runner
-template <int P>
-struct SegCtx {
-	FmState<P> st;
-	long long out_idx;      // next output slot (int16 index within the channel's output)
-	int nd;                 // decimated samples produced since the replay start
-	int first_in_chunk;     // next decimated sample is the first of its chunk (F8)
-	bool exact_start;       // state came from an exact carry, no bracket needed
-	bool emit;              // outputs are owned (t >= s0)
-};
-
-// Everything after the decimator for one decimated sample (di,dq).
-template <int P>
-__device__ __forceinline__ void back_end(const FmDev &c, const FmCall &k, SegCtx<P> &x, int16_t *__restrict__ out,
-                                         int di, int dq)
+// ------------------------------------------------------------------------------ bookkeeping
+// Decimated samples the reference has produced after t input samples of this call.
+__device__ __forceinline__ long long dec_before(const FmDev &c, long long t, int box_n0)
 {
-	FmState<P> &s = x.st;
-	if (c.fir_on) {
-		di = droop9(s.di, c.fir, di);
-		dq = droop9(s.dq, c.fir, dq);
-	}
-	const bool pcm_valid = x.exact_start || x.nd >= k.dec_exact;
-	if (!x.exact_start && x.nd == k.dec_exact) { s.lo = -32768; s.hi = 32767; s.dirty = 1; }
-	x.nd++;
-	int pcm;
-	if (c.mode == RXB200_MODE_FM) {
-		int br = s.pre_i, bj = s.pre_q;
-		int cr = add_w(mul_w(di, br), mul_w(dq, bj));       // x[n] * conj(x[n-1]) (src/rtl_fm.c:470-474)
-		int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
-		if (x.first_in_chunk || c.atan_mode == RXB200_ATAN_STD) { pcm = disc_std(cr, cj); }
-		else if (c.atan_mode == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
-		else if (c.atan_mode == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }
-		else { pcm = disc_ale(di, dq, br, bj); }
-		pcm = wrap16(pcm);
-		s.pre_i = di; s.pre_q = dq;
-	} else if (c.mode == RXB200_MODE_AM) {
-		int e = add_w(mul_w(di, di), mul_w(dq, dq));
-		pcm = wrap16(mul_w(wrap16((int)sqrt((double)e)), c.out_scale));
-	} else if (c.mode == RXB200_MODE_USB) {
-		pcm = wrap16(mul_w(wrap16(di + dq), c.out_scale));
-	} else if (c.mode == RXB200_MODE_LSB) {
-		pcm = wrap16(mul_w(wrap16(di - dq), c.out_scale));
-	} else {   // raw: lowpassed copied out, nothing after (src/rtl_fm.c:658-665, :809-811)
-		if (x.emit) { out[x.out_idx] = (int16_t)di; out[x.out_idx + 1] = (int16_t)dq; }
-		x.out_idx += 2;
-		x.first_in_chunk = 0;
-		s.dirty = pcm_valid ? 0 : 1;
-		return;
-	}
-	x.first_in_chunk = 0;
-	bool inexact = !pcm_valid;
-	if (c.deemph) {
-		bool same = (s.lo == s.hi);
-		s.lo = deemph_step(c, s.lo, pcm);
-		s.hi = same ? s.lo : deemph_step(c, s.hi, pcm);
-		pcm = wrap16(s.lo);
-		inexact = inexact || (s.lo != s.hi);
-	}
-	if (c.resample) {     // low_pass_real (src/rtl_fm.c:389-409)
-		if (inexact) { s.dirty = 1; }
-		s.lpr_acc = add_w(s.lpr_acc, pcm);
-		s.lpr_phase += c.slow;
-		if (s.lpr_phase >= c.fast) {
-			if (x.emit) { out[x.out_idx] = (int16_t)(s.lpr_acc / c.lpr_div); }
-			x.out_idx++;
-			s.lpr_phase -= c.fast;
-			s.lpr_acc = 0;
-			s.dirty = 0;
-		}
-	} else {
-		s.dirty = inexact ? 1 : 0;
-		if (x.emit) { out[x.out_idx] = (int16_t)pcm; }
-		x.out_idx++;
-	}
-}
-
-// One input sample at in-chunk index u.
-template <int P>
-__device__ __forceinline__ void front_end(const FmDev &c, const FmCall &k, SegCtx<P> &x, int16_t *__restrict__ out,
-                                          uint32_t w, unsigned u)
-{
-	int xi = scale_cs16(lo16(w));
-	int xq = scale_cs16(hi16(w));
-	if (!c.offset_tuning) {     // rotate16_90: sample n of the chunk times j^n (src/rtl_fm.c:309-327)
-		int ri, rq;
-		switch (u & 3u) {
-		case 1: ri = -xq; rq = xi; break;
-		case 2: ri = -xi; rq = -xq; break;
-		case 3: ri = xq; rq = -xi; break;
-		default: ri = xi; rq = xq; break;
-		}
-		xi = ri; xq = rq;
-	}
-	FmState<P> &s = x.st;
-	if constexpr (P == 0) {    // low_pass boxcar (src/rtl_fm.c:351-371)
-		s.box_i += xi; s.box_q += xq;
-		if (++s.box_n >= c.D) {
-			int di = wrap16(s.box_i), dq = wrap16(s.box_q);
-			s.box_i = 0; s.box_q = 0; s.box_n = 0;
-			back_end<P>(c, k, x, out, di, dq);
-		}
-	} else {
-		int di, dq;
-		if (cascade_push<0, P>(s, xi, xq, u, di, dq)) {
-			if ((u >> P) == 0u) { x.first_in_chunk = 1; }
-			back_end<P>(c, k, x, out, di, dq);
-		}
-	}
-}
-
-// Number of decimated samples the reference has produced after t input samples of this call.
-__device__ __forceinline__ long long dec_before(const FmDev &c, int P, long long t, int box_n0)
-{
-	if (P > 0) { return t >> P; }
+	if (c.P > 0) { return t >> c.P; }
 	return (t + box_n0) / c.D;
 }
-
-// Output slot of the first sample produced at/after decimated index m.
+// Output slot of the first value produced at/after decimated index m.
 __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int phase0)
 {
 	if (c.mode == RXB200_MODE_RAW) { return 2 * m; }
 	if (!c.resample) { return m; }
 	return ((long long)phase0 + m * (long long)c.slow) / (long long)c.fast;
 }
+// shared PCM buffer: 4 bytes of padding per 128 entries so that neither the front-end stores
+// (thread stride ~ Sf/D entries) nor the back-end loads (lane stride = piece) pile on one bank
+__device__ __forceinline__ int pcm_phys(int rel) { return rel + 2 * (rel >> 7); }
 
-// Runs [w0, s1) of channel ch; outputs are stored for t >= s0.  If from_exact the state in x.st is
-// the exact state at w0 (carry or a neighbour's end state).  Returns flags: bit0 = state was exact
-// when the owned part began, bit1 = state exact at the end.
+struct EmitCtx {
+	int16_t *pcm;            // shared PCM buffer
+	int16_t *out;            // channel output (direct_out only)
+	long long m;             // decimated index of the next sample
+	long long m_lo;          // decimated index of pcm[0]
+	int first_in_chunk;
+	bool store;              // emission belongs to this thread's own segment
+};
+
+// Everything between the decimator and the serial stages, for one decimated sample.
 template <int P>
-__device__ int run_segment(const FmDev &c, const FmCall &k, SegCtx<P> &x, int ch, long long w0, long long s0,
-                           long long s1, int box_n0, int phase0, bool from_exact)
+__device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e, int di, int dq)
 {
-	const uint4 *__restrict__ in4 = reinterpret_cast<const uint4 *>(k.in + 2 * (size_t)ch * (size_t)k.n);
-	int16_t *__restrict__ out = k.out + (size_t)ch * (size_t)k.out_stride;
-	FmState<P> &s = x.st;
-	x.exact_start = from_exact;
-	x.nd = 0;
-	// position bookkeeping at w0
-	unsigned u = (unsigned)(w0 % k.chunk);
-	long long chunk_base = w0 - u;
-	long long m0 = dec_before(c, P, w0, box_n0);
-	if (!from_exact) {
-		if (P == 0) { s.box_n = (int)((w0 + box_n0) % c.D); }
-		if (c.resample) { s.lpr_phase = (int)(((long long)phase0 + m0 * (long long)c.slow) % (long long)c.fast); }
+	if (c.fir_on) {
+		di = droop9(s.di, c.fir, di);
+		dq = droop9(s.dq, c.fir, dq);
 	}
-	x.out_idx = out_before(c, m0, phase0);
-	// boxcar: is the next decimated sample the first of its chunk?
-	if (P == 0) { x.first_in_chunk = (dec_before(c, P, chunk_base, box_n0) == m0) ? 1 : 0; }
-	else { x.first_in_chunk = 0; }
-	int flags = from_exact ? 1 : 0;
-	x.emit = false;
-	for (long long t = w0; t < s1; t += 8) {
-		if (t == s0) {
-			x.emit = true;
-			if (!from_exact) {
-				bool ok = (x.nd >= k.dec_exact) && !s.dirty && (!c.deemph || s.lo == s.hi);
-				flags = ok ? 1 : 0;
+	int pcm;
+	if (c.mode == RXB200_MODE_FM) {
+		int br = s.pre_i, bj = s.pre_q;
+		int cr = add_w(mul_w(di, br), mul_w(dq, bj));       // x[n] * conj(x[n-1]) (src/rtl_fm.c:470-474)
+		int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
+		if (e.first_in_chunk || c.atan_mode == RXB200_ATAN_STD) { pcm = disc_std(cr, cj); }   // F8
+		else if (c.atan_mode == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
+		else if (c.atan_mode == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }
+		else { pcm = disc_ale(di, dq, br, bj); }
+		pcm = wrap16(pcm);
+		s.pre_i = di; s.pre_q = dq;
+	} else if (c.mode == RXB200_MODE_AM) {
+		int en = add_w(mul_w(di, di), mul_w(dq, dq));
+		pcm = wrap16(mul_w(wrap16((int)sqrt((double)en)), c.out_scale));
+	} else if (c.mode == RXB200_MODE_USB) {
+		pcm = wrap16(mul_w(wrap16(di + dq), c.out_scale));
+	} else if (c.mode == RXB200_MODE_LSB) {
+		pcm = wrap16(mul_w(wrap16(di - dq), c.out_scale));
+	} else {   // raw: lowpassed copied out, nothing after (src/rtl_fm.c:658-665, :809-811)
+		if (e.store) { e.out[2 * e.m] = (int16_t)di; e.out[2 * e.m + 1] = (int16_t)dq; }
+		e.m++;
+		e.first_in_chunk = 0;
+		return;
+	}
+	e.first_in_chunk = 0;
+	if (e.store) {
+		if (k.direct_out) { e.out[e.m] = (int16_t)pcm; }
+		else { e.pcm[pcm_phys((int)(e.m - e.m_lo))] = (int16_t)pcm; }
+	}
+	e.m++;
+}
+
+// scale + fs/4 rotation of one CS16 word (I low, Q high): rotate16_90 multiplies sample n of the chunk by
+// j^n (src/rtl_fm.c:309-327); pos = n & 3 is a compile-time constant in the unrolled block.
+__device__ __forceinline__ void scale_rot(uint32_t w, int pos, bool rotate, int &ri, int &rq)
+{
+	int xi = scale_cs16(lo16(w)), xq = scale_cs16(hi16(w));
+	if (!rotate) { pos = 0; }
+	switch (pos & 3) {
+	case 1: ri = -xq; rq = xi; break;
+	case 2: ri = -xi; rq = -xq; break;
+	case 3: ri = xq; rq = -xi; break;
+	default: ri = xi; rq = xq; break;
+	}
+}
+__device__ __forceinline__ uint32_t scale_rot_pack(uint32_t w, int pos, bool rotate)
+{
+	int ri, rq;
+	scale_rot(w, pos, rotate, ri, rq);
+	return (uint32_t)(ri + 128) + ((uint32_t)(rq + 128) << 16);
+}
+
+__device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
+{
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+	             : "l"(p));
+}
+
+// One block of 8 input samples at in-chunk offset u (multiple of 8).
+template <int P>
+__device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
+                                            const uint32_t (&v)[8], unsigned u)
+{
+	constexpr int PL = FrontState<P>::PL;
+	const bool rot = !c.offset_tuning;
+	if constexpr (P == 0) {
+		// low_pass boxcar (src/rtl_fm.c:351-371)
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int xi, xq;
+			scale_rot(v[j], j, rot, xi, xq);
+			s.box_i += xi; s.box_q += xq;
+			if (++s.box_n >= c.D) {
+				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
+				s.box_i = 0; s.box_q = 0; s.box_n = 0;
+				post_decim<P>(c, k, s, e, di, dq);
 			}
 		}
-		uint4 a = __ldg(in4 + (t >> 2));
-		uint4 b = __ldg(in4 + (t >> 2) + 1);
-		if (P == 0 && u == 0u) { x.first_in_chunk = 1; }
-		const unsigned ub = u;     // multiple of 8
-		front_end<P>(c, k, x, out, a.x, ub | 0u);
-		front_end<P>(c, k, x, out, a.y, ub | 1u);
-		front_end<P>(c, k, x, out, a.z, ub | 2u);
-		front_end<P>(c, k, x, out, a.w, ub | 3u);
-		front_end<P>(c, k, x, out, b.x, ub | 4u);
-		front_end<P>(c, k, x, out, b.y, ub | 5u);
-		front_end<P>(c, k, x, out, b.z, ub | 6u);
-		front_end<P>(c, k, x, out, b.w, ub | 7u);
-		u += 8u;
-		if (u >= (unsigned)k.chunk) { u = 0u; }
+	} else {
+		uint32_t x[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) { x[j] = scale_rot_pack(v[j], j, rot); }
+		// pass 0: window for the sample at block offset 2j is s[2j-5 .. 2j] of (h[0] .. , x[0..7])
+		uint32_t (&h0)[6] = s.h[0];
+		uint32_t y[4];
+		y[0] = hb_tap(h0[1], h0[2], h0[3], h0[4], h0[5], x[0]);
+		y[1] = hb_tap(h0[3], h0[4], h0[5], x[0], x[1], x[2]);
+		y[2] = hb_tap(h0[5], x[0], x[1], x[2], x[3], x[4]);
+		y[3] = hb_tap(x[1], x[2], x[3], x[4], x[5], x[6]);
+#pragma unroll
+		for (int j = 0; j < 6; j++) { h0[j] = x[j + 2]; }
+		uint32_t outw[4];
+		int nout;
+		if constexpr (PL == 1) {
+			outw[0] = y[0]; outw[1] = y[1]; outw[2] = y[2]; outw[3] = y[3];
+			nout = 4;
+		} else {
+			uint32_t (&h1)[6] = s.h[1];
+			uint32_t z0 = hb_tap(h1[1], h1[2], h1[3], h1[4], h1[5], y[0]);
+			uint32_t z1 = hb_tap(h1[3], h1[4], h1[5], y[0], y[1], y[2]);
+			h1[0] = h1[4]; h1[1] = h1[5]; h1[2] = y[0]; h1[3] = y[1]; h1[4] = y[2]; h1[5] = y[3];
+			if constexpr (PL == 2) {
+				outw[0] = z0; outw[1] = z1;
+				nout = 2;
+			} else {
+				uint32_t (&h2)[6] = s.h[2];
+				outw[0] = hb_tap(h2[1], h2[2], h2[3], h2[4], h2[5], z0);
+				h2[0] = h2[2]; h2[1] = h2[3]; h2[2] = h2[4]; h2[3] = h2[5]; h2[4] = z0; h2[5] = z1;
+				nout = 1;
+			}
+		}
+		const int bias = 128 << PL;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (j < nout) {
+				int di = (int)(outw[j] & 0xffffu) - bias, dq = (int)(outw[j] >> 16) - bias;
+				if constexpr (P > PL) {
+					// in-chunk index of this sample at pass PL: (u >> PL) + j
+					int oi, oq;
+					if (scalar_push<0, P>(s, di, dq, (u >> PL) + (unsigned)j, oi, oq)) { post_decim<P>(c, k, s, e, oi, oq); }
+				} else {
+					post_decim<P>(c, k, s, e, di, dq);
+				}
+			}
+		}
 	}
-	bool end_ok = from_exact || ((flags & 1) != 0) ||
-	              ((x.nd >= k.dec_exact) && !s.dirty && (!c.deemph || s.lo == s.hi));
-	if (end_ok) { flags |= 2; }
-	return flags;
+}
+
+// ------------------------------------------------------------------------------ back end
+struct BackState { int lo, hi, acc, phase, dirty; };
+
+// One PCM sample through deemph + low_pass_real; returns true when the bracket is open.
+__device__ __forceinline__ void back_step(const FmDev &c, BackState &b, int pcm, bool valid, bool emit,
+                                          int16_t *__restrict__ out, long long &oidx)
+{
+	bool inexact = !valid;
+	if (c.deemph) {
+		bool same = (b.lo == b.hi);
+		b.lo = deemph_step(c, b.lo, pcm);
+		b.hi = same ? b.lo : deemph_step(c, b.hi, pcm);
+		pcm = wrap16(b.lo);
+		inexact = inexact || (b.lo != b.hi);
+	}
+	if (c.resample) {     // low_pass_real (src/rtl_fm.c:389-409)
+		if (inexact) { b.dirty = 1; }
+		b.acc = add_w(b.acc, pcm);
+		b.phase += c.slow;
+		if (b.phase >= c.fast) {
+			if (emit) { out[oidx] = (int16_t)(b.acc / c.lpr_div); }
+			oidx++;
+			b.phase -= c.fast;
+			b.acc = 0;
+			b.dirty = 0;
+		}
+	} else {
+		b.dirty = inexact ? 1 : 0;
+		if (emit) { out[oidx] = (int16_t)pcm; }
+		oidx++;
+	}
 }
 
 template <int P>
-__global__ void __launch_bounds__(128) fm_main_kernel(const FmDev c, const FmCall k)
+__global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, const FmCall k)
 {
-	long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (long long)k.n_ch * k.nseg) { return; }
-	int ch = (int)(gid / k.nseg);
-	int seg = (int)(gid % k.nseg);
-	long long s0 = (long long)seg * k.S;
-	long long s1 = s0 + k.S < k.n ? s0 + k.S : k.n;
-	long long w0 = s0 - k.warm;
-	const uint32_t *carry = k.carry_in + (size_t)ch * k.state_words;
-	const int box_n0 = (int)carry[ST_BOX_N];
-	const int phase0 = (int)carry[ST_LPR_PHASE];
-	SegCtx<P> x;
-	bool from_exact = (w0 <= 0);
-	if (from_exact) { w0 = 0; state_load<P>(x.st, carry); }
-	else { state_zero<P>(x.st); }
-	int flags = run_segment<P>(c, k, x, ch, w0, s0, s1, box_n0, phase0, from_exact);
-	uint32_t *dst = k.seg_state + (size_t)gid * k.state_words;
-	state_store<P>(x.st, dst);
-	k.seg_flags[gid] = flags;
-	if (seg == k.nseg - 1) { state_store<P>(x.st, k.carry_out + (size_t)ch * k.state_words); }
-}
+	extern __shared__ __align__(16) int16_t pcm_s[];
+	__shared__ int s_work;
+	const int tid = threadIdx.x;
+	const int total_work = k.n_ch * k.n_cta;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) { s_work = atomicAdd(k.ticket, 1); }
+		__syncthreads();
+		const int work = s_work;
+		if (work >= total_work) { break; }
+		const int ch = work / k.n_cta;
+		const int b = work % k.n_cta;
+		const uint32_t *carry = k.carry_in + (size_t)ch * k.state_words;
+		const int box_n0 = (int)carry[ST_BOX_N];
+		const int phase0 = (int)carry[ST_LPR_PHASE];
+		const int16_t *__restrict__ in = k.in + 2 * (size_t)ch * (size_t)k.n;
+		int16_t *__restrict__ out = k.out + (size_t)ch * (size_t)k.out_stride;
+		const long long own_lo = (long long)b * k.n_own * k.Sf;
+		long long own_hi = own_lo + (long long)k.n_own * k.Sf;
+		if (own_hi > k.n) { own_hi = k.n; }
+		long long buf_lo = own_lo - (long long)k.n_extra * k.Sf;
+		if (buf_lo < 0) { buf_lo = 0; }
+		const long long m_lo = dec_before(c, buf_lo, box_n0);
+		const long long m_own = dec_before(c, own_lo, box_n0);
+		const long long m_hi = dec_before(c, own_hi, box_n0);
 
-// Serial repair of segments whose de-emphasis bracket had not closed at their start.  Thread g
-// acts only if segment g failed and segment g-1 ended exact; it then walks right until it has
-// re-run a segment whose ORIGINAL end state was already exact (its right neighbour is either
-// fine or has its own repair thread).
-template <int P>
-__global__ void __launch_bounds__(128) fm_fixup_kernel(const FmDev c, const FmCall k)
-{
-	long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (long long)k.n_ch * k.nseg) { return; }
-	int ch = (int)(gid / k.nseg);
-	int seg = (int)(gid % k.nseg);
-	if (seg == 0) { return; }
-	if (k.seg_flags[gid] & 1) { return; }
-	if (!(k.seg_flags[gid - 1] & 2)) { return; }
-	const uint32_t *carry = k.carry_in + (size_t)ch * k.state_words;
-	const int box_n0 = (int)carry[ST_BOX_N];
-	const int phase0 = (int)carry[ST_LPR_PHASE];
-	SegCtx<P> x;
-	for (int sgi = seg; sgi < k.nseg; sgi++) {
-		long long g = (long long)ch * k.nseg + sgi;
-		int orig = k.seg_flags[g];
-		if (sgi != seg && (orig & 1)) { break; }
-		long long s0 = (long long)sgi * k.S;
-		long long s1 = s0 + k.S < k.n ? s0 + k.S : k.n;
-		state_load<P>(x.st, k.seg_state + (size_t)(g - 1) * k.state_words);
-		run_segment<P>(c, k, x, ch, s0, s0, s1, box_n0, phase0, true);
-		state_store<P>(x.st, k.seg_state + (size_t)g * k.state_words);
-		if (sgi == k.nseg - 1) { state_store<P>(x.st, k.carry_out + (size_t)ch * k.state_words); }
-		atomicAdd(k.fix_count, 1);
-		if (orig & 2) { break; }
+		// ---------------- front end: one segment per thread
+		{
+			const long long g = (long long)b * k.n_own + (tid - k.n_extra);
+			const long long start = g * k.Sf;
+			if (g >= 0 && start < k.n) {
+				long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
+				long long t0 = start - k.halo;
+				FrontState<P> s;
+				if (t0 <= 0) { t0 = 0; front_load<P>(s, carry); }
+				else {
+					front_zero<P>(s);
+					if (P == 0) { s.box_n = (int)((t0 + box_n0) % c.D); }
+				}
+				unsigned u = (unsigned)(t0 % k.chunk);
+				EmitCtx e;
+				e.pcm = pcm_s; e.out = out; e.m_lo = m_lo;
+				e.m = dec_before(c, t0, box_n0);
+				e.first_in_chunk = 0;
+				if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, box_n0) == e.m) ? 1 : 0; }
+				e.store = false;
+				for (long long t = t0; t < end; t += 8) {
+					if (u >= (unsigned)k.chunk) { u = 0u; }
+					if (u == 0u) {
+						e.first_in_chunk = 1;
+						// chunk start: every pass forgets the odd sample it was holding
+#pragma unroll
+						for (int l = 0; l < FrontState<P>::PL; l++) {
+#pragma unroll
+							for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
+						}
+					}
+					if (t >= start) { e.store = true; }
+					uint32_t v[8];
+					ldg256(in + 2 * t, v);
+					front_block<P>(c, k, s, e, v, u);
+					u += 8u;
+				}
+				if (end == k.n) {
+					// this thread saw the end of the stream: its registers are the next call's carry
+					front_store<P>(s, k.carry_out + (size_t)ch * k.state_words);
+				}
+			}
+		}
+		if (k.direct_out) {
+			if (tid == 0 && b == k.n_cta - 1) {
+				uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
+				co[ST_AVG] = carry[ST_AVG]; co[ST_LPR_ACC] = carry[ST_LPR_ACC]; co[ST_LPR_PHASE] = carry[ST_LPR_PHASE];
+				co[ST_SQ_HITS] = carry[ST_SQ_HITS];
+			}
+			continue;
+		}
+		__syncthreads();
+
+		// ---------------- back end: warp 0, one contiguous piece of the CTA's PCM per lane
+		if (tid < 32) {
+			const int lane = tid;
+			const long long count = m_hi - m_own;
+			long long piece = (count + 31) / 32;
+			piece += (2 - (piece & 3) + 4) & 3;          // piece = 2 (mod 4): lane stride is an odd number of words
+			if (piece < 2) { piece = 2; }
+			const long long p0 = m_own + (long long)lane * piece;
+			long long p1 = p0 + piece;
+			if (p1 > m_hi) { p1 = m_hi; }
+			const bool active = p0 < m_hi;
+			const int last_lane = count > 0 ? (int)((count - 1) / piece) : 0;
+			BackState bs;
+			bs.lo = -32768; bs.hi = 32767; bs.acc = 0; bs.phase = 0; bs.dirty = 1;
+			long long oidx = 0;
+			bool start_ok = true;
+			if (active) {
+				long long ms = p0 - k.W_dec;
+				if (ms < m_lo) { ms = m_lo; }
+				const bool exact = (ms == 0);                 // start of the call: the carry is the state
+				if (exact) { bs.lo = bs.hi = (int)carry[ST_AVG]; bs.acc = (int)carry[ST_LPR_ACC]; bs.dirty = 0; }
+				if (!c.deemph) { bs.lo = bs.hi = 0; }
+				if (c.resample) { bs.phase = (int)(((long long)phase0 + ms * (long long)c.slow) % (long long)c.fast); }
+				oidx = out_before(c, ms, phase0);
+				for (long long m = ms; m < p0; m++) {
+					back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, false, out, oidx);
+				}
+				start_ok = exact || (!bs.dirty && bs.lo == bs.hi);
+				for (long long m = p0; m < p1; m++) {
+					back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, true, out, oidx);
+				}
+			}
+			// resolve lanes whose bracket was still open at their piece start
+			bool need = active && !start_ok;
+			bool end_exact = !active || start_ok || (!bs.dirty && bs.lo == bs.hi);
+			int pred_avg = 0, pred_acc = 0;
+			bool have_pred = false;
+			for (int round = 0; round < 34; round++) {
+				unsigned need_mask = __ballot_sync(0xffffffffu, need);
+				if (need_mask == 0u) { break; }
+				int up_avg = __shfl_up_sync(0xffffffffu, bs.lo, 1);
+				int up_acc = __shfl_up_sync(0xffffffffu, bs.acc, 1);
+				int up_ok = __shfl_up_sync(0xffffffffu, end_exact ? 1 : 0, 1);
+				bool can = false;
+				if (need) {
+					if (lane == 0) {
+						// left neighbour is the previous CTA of this channel (older ticket): wait for its end state
+						if (!have_pred) {
+							volatile int *pp = k.pub + 4 * (size_t)(work - 1);
+							while (pp[0] == 0) { __nanosleep(64); }
+							__threadfence();
+							pred_avg = pp[1]; pred_acc = pp[2];
+							have_pred = true;
+						}
+						can = true;
+					} else if (up_ok) {
+						pred_avg = up_avg; pred_acc = up_acc;
+						can = true;
+					}
+				}
+				if (can) {
+					bs.lo = bs.hi = c.deemph ? pred_avg : 0;
+					bs.acc = pred_acc; bs.dirty = 0;
+					if (c.resample) { bs.phase = (int)(((long long)phase0 + p0 * (long long)c.slow) % (long long)c.fast); }
+					oidx = out_before(c, p0, phase0);
+					for (long long m = p0; m < p1; m++) {
+						back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, true, out, oidx);
+					}
+					need = false; end_exact = true;
+					atomicAdd(k.fix_count, 1);
+				}
+			}
+			// publish this CTA's end state for its right neighbour; the last CTA writes the carry
+			int fin_avg = __shfl_sync(0xffffffffu, bs.lo, last_lane);
+			int fin_acc = __shfl_sync(0xffffffffu, bs.acc, last_lane);
+			int fin_phase = __shfl_sync(0xffffffffu, bs.phase, last_lane);
+			if (lane == 0) {
+				if (count <= 0) {
+					// nothing decimated in this stretch: hand the neighbour's state through
+					if (b == 0) { fin_avg = (int)carry[ST_AVG]; fin_acc = (int)carry[ST_LPR_ACC]; }
+					else {
+						volatile int *pp = k.pub + 4 * (size_t)(work - 1);
+						while (pp[0] == 0) { __nanosleep(64); }
+						__threadfence();
+						fin_avg = pp[1]; fin_acc = pp[2];
+					}
+					fin_phase = c.resample ? (int)(((long long)phase0 + m_hi * (long long)c.slow) % (long long)c.fast) : 0;
+				}
+				volatile int *mp = k.pub + 4 * (size_t)work;
+				mp[1] = fin_avg; mp[2] = fin_acc;
+				__threadfence();
+				mp[0] = 1;
+				if (b == k.n_cta - 1) {
+					uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
+					co[ST_AVG] = (uint32_t)fin_avg; co[ST_LPR_ACC] = (uint32_t)fin_acc; co[ST_LPR_PHASE] = (uint32_t)fin_phase;
+					co[ST_SQ_HITS] = carry[ST_SQ_HITS];
+				}
+			}
+		}
 	}
 }
 
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
-template <int P> struct KernelPair { static fm_kernel_fn main_k() { return fm_main_kernel<P>; } static fm_kernel_fn fix_k() { return fm_fixup_kernel<P>; } };
-
-static void pick_kernels(int P, fm_kernel_fn *mk, fm_kernel_fn *fk)
+static fm_kernel_fn pick_kernel(int P)
 {
 	switch (P) {
-#define RXB_CASE(N) case N: *mk = KernelPair<N>::main_k(); *fk = KernelPair<N>::fix_k(); break;
-	RXB_CASE(0) RXB_CASE(1) RXB_CASE(2) RXB_CASE(3) RXB_CASE(4) RXB_CASE(5)
-	RXB_CASE(6) RXB_CASE(7) RXB_CASE(8) RXB_CASE(9) RXB_CASE(10)
-#undef RXB_CASE
-	default: *mk = nullptr; *fk = nullptr;
+	case 0: return fm_fused_kernel<0>;
+	case 1: return fm_fused_kernel<1>;
+	case 2: return fm_fused_kernel<2>;
+	case 3: return fm_fused_kernel<3>;
+	case 4: return fm_fused_kernel<4>;
+	case 5: return fm_fused_kernel<5>;
+	case 6: return fm_fused_kernel<6>;
+	case 7: return fm_fused_kernel<7>;
+	case 8: return fm_fused_kernel<8>;
+	case 9: return fm_fused_kernel<9>;
+	case 10: return fm_fused_kernel<10>;
+	default: return nullptr;
 	}
 }
 
@@ -507,14 +690,13 @@ struct rxb200_fm {
 	rxb200_fm_params p;
 	int device;
 	int n_channels;
+	int n_sm;
 	FmDev dev;
 	int state_words;
 	cudaStream_t stream;
 	uint32_t *d_carry[2];
 	int cur;                       // which carry buffer holds the current state
-	uint32_t *d_seg_state; size_t seg_state_cap;   // words
-	int *d_seg_flags; size_t seg_flags_cap;
-	int *d_fix_count;
+	int *d_sync; size_t sync_cap;  // [0] ticket, [1] fix_count, [4..] pub[n_ch*n_cta][4]
 	int *d_atan_lut;
 	int16_t *d_in; size_t d_in_cap;                // int16 elements
 	int16_t *d_out; size_t d_out_cap;
@@ -523,7 +705,8 @@ struct rxb200_fm {
 	int h_lpr_phase;               // demod.prev_lpr_index
 	int tune_seg, tune_warm;
 	rxb200_fm_stats stats;
-	fm_kernel_fn main_k, fix_k;
+	fm_kernel_fn kern;
+	int smem_optin;
 	cudaEvent_t ev0, ev1;
 };
 
@@ -550,12 +733,13 @@ static void fm_fill_dev(rxb200_fm *h)
 	const rxb200_fm_params &p = h->p;
 	FmDev &d = h->dev;
 	memset(&d, 0, sizeof d);
-	d.mode = p.mode; d.P = p.downsample_passes; d.D = p.downsample_passes ? (1 << p.downsample_passes) : p.downsample;
+	d.mode = p.mode; d.P = p.downsample_passes; d.PL = fm_packed_levels(d.P);
+	d.D = p.downsample_passes ? (1 << p.downsample_passes) : p.downsample;
 	d.fir_on = (p.downsample_passes > 0 && p.comp_fir_size == 9) ? 1 : 0;
 	d.atan_mode = p.custom_atan; d.out_scale = p.output_scale; d.post_ds = p.post_downsample;
 	d.deemph = (p.deemph && p.mode != RXB200_MODE_RAW) ? 1 : 0;
 	d.a = p.deemph ? p.deemph_a : 1; d.a_half = d.a / 2; d.a_even = (d.a % 2 == 0) ? 1 : 0;
-	// reciprocal for floor(n/a), n in [0, 2^19): verified exhaustively, else fall back to '/'
+	// reciprocal for floor(n/a) over the numerator range used: verified exhaustively, else fall back to '/'
 	d.a_use_magic = 0;
 	if (d.a >= 1 && d.a < 16384) {
 		unsigned magic = (unsigned)(0x100000000ULL / (unsigned)d.a) + 1u;
@@ -589,14 +773,17 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	memset(h, 0, sizeof *h);
 	h->p = *params; h->device = device; h->n_channels = n_channels;
 	h->state_words = fm_state_words(params->downsample_passes);
-	pick_kernels(params->downsample_passes, &h->main_k, &h->fix_k);
+	h->kern = pick_kernel(params->downsample_passes);
+	cudaDeviceProp prop;
+	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
+	h->n_sm = prop.multiProcessorCount;
+	h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	RXB_CUDA(cudaEventCreate(&h->ev0));
 	RXB_CUDA(cudaEventCreate(&h->ev1));
 	size_t cbytes = (size_t)n_channels * h->state_words * sizeof(uint32_t);
 	RXB_CUDA(cudaMalloc(&h->d_carry[0], cbytes));
 	RXB_CUDA(cudaMalloc(&h->d_carry[1], cbytes));
-	RXB_CUDA(cudaMalloc(&h->d_fix_count, sizeof(int)));
 	if (params->custom_atan == RXB200_ATAN_LUT && params->mode == RXB200_MODE_FM) {
 		// atan_lut_init (src/rtl_fm.c:515-526): host libm, uploaded once
 		std::vector<int> lut(131072);
@@ -614,12 +801,19 @@ extern "C" int rxb200_fm_reset(rxb200_fm *h)
 	if (!h) { return RXB200_EINVAL; }
 	RXB_CUDA(cudaSetDevice(h->device));
 	size_t cbytes = (size_t)h->n_channels * h->state_words * sizeof(uint32_t);
-	RXB_CUDA(cudaMemsetAsync(h->d_carry[0], 0, cbytes, h->stream));
-	RXB_CUDA(cudaMemsetAsync(h->d_carry[1], 0, cbytes, h->stream));
-	// squelch_hits starts at 11 (demod_init, src/rtl_fm.c:1091)
+	// demod_init (src/rtl_fm.c:1084-1115): everything zero, squelch_hits 11.  A zero sample in a
+	// packed fifth_order history is its bias.
 	std::vector<uint32_t> init((size_t)h->n_channels * h->state_words, 0u);
-	for (int c = 0; c < h->n_channels; c++) { init[(size_t)c * h->state_words + ST_SQ_HITS] = 11u; }
+	const int PL = fm_packed_levels(h->p.downsample_passes);
+	for (int c = 0; c < h->n_channels; c++) {
+		uint32_t *s = &init[(size_t)c * h->state_words];
+		s[ST_SQ_HITS] = 11u;
+		for (int l = 0; l < PL; l++) {
+			for (int j = 0; j < 6; j++) { s[ST_HDR + 6 * l + j] = 0x00010001u * (128u << l); }
+		}
+	}
 	RXB_CUDA(cudaMemcpyAsync(h->d_carry[0], init.data(), cbytes, cudaMemcpyHostToDevice, h->stream));
+	RXB_CUDA(cudaMemcpyAsync(h->d_carry[1], init.data(), cbytes, cudaMemcpyHostToDevice, h->stream));
 	RXB_CUDA(cudaStreamSynchronize(h->stream));
 	h->cur = 0; h->h_box_n = 0; h->h_lpr_phase = 0;
 	return RXB200_OK;
@@ -630,8 +824,8 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 	if (!h) { return; }
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_seg_state); cudaFree(h->d_seg_flags);
-	cudaFree(h->d_fix_count); cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
+	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_sync);
+	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -673,7 +867,6 @@ static size_t fm_count_outputs(rxb200_fm *h, size_t n_int16, size_t chunk_int16,
 extern "C" size_t rxb200_fm_max_output(const rxb200_fm *h, size_t n_int16, size_t chunk_int16)
 {
 	if (!h || chunk_int16 == 0) { return 0; }
-	(void)chunk_int16;
 	const rxb200_fm_params &p = h->p;
 	size_t L = n_int16 / 2;
 	size_t D = p.downsample_passes ? ((size_t)1 << p.downsample_passes) : (size_t)p.downsample;
@@ -699,66 +892,87 @@ static int fm_check_shape(const rxb200_fm *h, size_t n_int16, size_t chunk_int16
 	return RXB200_OK;
 }
 
+static long long round_up_ll(long long v, long long g) { return ((v + g - 1) / g) * g; }
+
 static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t chunk_int16, int16_t *d_out,
                      size_t out_stride)
 {
 	const rxb200_fm_params &p = h->p;
+	const FmDev &dv = h->dev;
 	const long long n = (long long)(n_int16 / 2);
 	const int P = p.downsample_passes;
-	const long long Dtot = P ? (1LL << P) : p.downsample;
+	const long long Dtot = dv.D;
 	const long long G = (1LL << P) > 8 ? (1LL << P) : 8;
-	// replay length in decimated samples: front-end flush, de-emphasis bracket, one resampler group
-	int dec_exact = P ? 26 : 3;
+	// front-end replay: decimated samples until cascade (6) + droop FIR (9) + discriminator (1) are exact
+	const long long dec_exact = P ? 18 : 3;
+	const long long halo = round_up_ll(dec_exact * Dtot, G);
+	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample)) ? 1 : 0;
+	// back-end replay (decimated samples): de-emphasis bracket + one resampler group
 	long long wd = 0;
-	if (h->dev.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
-	long long warm_dec = dec_exact + wd + (h->dev.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
-	long long warm = ((warm_dec * Dtot + G - 1) / G) * G;
-	long long S;
-	if (h->tune_seg > 0) { S = h->tune_seg; }
-	else {
-		const char *e = getenv("RXB200_FM_SEG");
-		S = e ? atoll(e) : 0;
-		if (S <= 0) {
-			long long want = (n * h->n_channels) / (148LL * 384LL);
-			S = want > 3 * warm ? want : 3 * warm;
+	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
+	const long long W_dec = direct_out ? 0 : wd + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
+	// segment per thread: ~128 decimated samples, at least 4 halos, capped so the PCM buffer stays small
+	long long Sf = h->tune_seg;
+	if (Sf <= 0) { const char *e = getenv("RXB200_FM_SEG"); Sf = e ? atoll(e) : 0; }
+	if (Sf <= 0) {
+		Sf = 128 * Dtot;
+		if (Sf > 2048) { Sf = 2048; }
+		if (Sf < 4 * halo) { Sf = 4 * halo; }
+	}
+	Sf = round_up_ll(Sf, G);
+	long long n_extra, n_own, stretch, n_cta, ppt, pcm_cap;
+	size_t smem;
+	for (;;) {
+		n_extra = direct_out ? 0 : ((W_dec + 2) * Dtot + halo + Sf - 1) / Sf;
+		ppt = Sf / Dtot + 2;
+		pcm_cap = direct_out ? 8 : (long long)FM_THREADS * ppt + 64;
+		pcm_cap += 2 * (pcm_cap >> 7) + 8;
+		smem = (size_t)pcm_cap * sizeof(int16_t);
+		if (n_extra > FM_THREADS / 2 && (long long)smem * 2 <= h->smem_optin) {
+			Sf = round_up_ll(Sf * 2, G);          // very long warm-up: lengthen the segments
+			continue;
 		}
+		if ((long long)smem > h->smem_optin && Sf > G) {
+			Sf = round_up_ll(Sf / 2, G);          // PCM buffer too large: shorten the segments
+			if (((W_dec + 2) * Dtot + halo + Sf - 1) / Sf <= FM_THREADS / 2) { continue; }
+		}
+		break;
 	}
-	S = ((S + G - 1) / G) * G;
-	if (S < G) { S = G; }
-	long long nseg = (n + S - 1) / S;
-	if (nseg < 1) { nseg = 1; }
-	size_t total_seg = (size_t)nseg * h->n_channels;
-	size_t need_words = total_seg * h->state_words;
-	if (need_words > h->seg_state_cap) {
-		cudaFree(h->d_seg_state); h->d_seg_state = nullptr; h->seg_state_cap = 0;
-		RXB_CUDA(cudaMalloc(&h->d_seg_state, need_words * sizeof(uint32_t)));
-		h->seg_state_cap = need_words;
+	if ((long long)smem > h->smem_optin || n_extra >= FM_THREADS) {
+		set_error("no segment length fits: warm-up %lld samples, D=%lld, shared memory %d", (W_dec + 2) * Dtot, Dtot, h->smem_optin);
+		return RXB200_EUNSUPPORTED;
 	}
-	if (total_seg > h->seg_flags_cap) {
-		cudaFree(h->d_seg_flags); h->d_seg_flags = nullptr; h->seg_flags_cap = 0;
-		RXB_CUDA(cudaMalloc(&h->d_seg_flags, total_seg * sizeof(int)));
-		h->seg_flags_cap = total_seg;
+	n_own = FM_THREADS - n_extra;
+	stretch = n_own * Sf;
+	n_cta = (n + stretch - 1) / stretch;
+	const size_t total_work = (size_t)n_cta * h->n_channels;
+	const size_t need_sync = 4 + 4 * total_work;
+	if (need_sync > h->sync_cap) {
+		cudaFree(h->d_sync); h->d_sync = nullptr; h->sync_cap = 0;
+		RXB_CUDA(cudaMalloc(&h->d_sync, need_sync * sizeof(int)));
+		h->sync_cap = need_sync;
 	}
+	RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
 	FmCall k;
+	memset(&k, 0, sizeof k);
 	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
-	k.n_ch = h->n_channels; k.S = (int)S; k.warm = (int)warm; k.dec_exact = dec_exact; k.nseg = (int)nseg;
+	k.n_ch = h->n_channels; k.Sf = (int)Sf; k.halo = (int)halo; k.n_extra = (int)n_extra; k.n_own = (int)n_own;
+	k.n_cta = (int)n_cta; k.W_dec = (int)W_dec; k.pcm_cap = (int)pcm_cap; k.direct_out = direct_out;
 	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
-	k.seg_state = h->d_seg_state; k.seg_flags = h->d_seg_flags; k.fix_count = h->d_fix_count;
-	RXB_CUDA(cudaMemsetAsync(h->d_fix_count, 0, sizeof(int), h->stream));
-	unsigned blocks = (unsigned)((total_seg + 127) / 128);
+	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
+	RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
+	if (per_sm < 1) { per_sm = 1; }
+	size_t blocks = (size_t)h->n_sm * per_sm;
+	if (blocks > total_work) { blocks = total_work; }
 	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
-	h->main_k<<<blocks, 128, 0, h->stream>>>(h->dev, k);
+	h->kern<<<(unsigned)blocks, FM_THREADS, smem, h->stream>>>(dv, k);
 	RXB_CUDA(cudaGetLastError());
 	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
-	int launches = 1;
-	if (nseg > 1) {
-		h->fix_k<<<blocks, 128, 0, h->stream>>>(h->dev, k);
-		RXB_CUDA(cudaGetLastError());
-		launches++;
-	}
 	h->cur ^= 1;
-	h->stats.launches = launches; h->stats.segments = (int)total_seg; h->stats.segment_len = (int)S;
-	h->stats.warmup_len = (int)warm; h->stats.fixup_segments = -1;
+	h->stats.launches = 1; h->stats.segments = (int)(total_work * FM_THREADS); h->stats.segment_len = (int)Sf;
+	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1;
 	return RXB200_OK;
 }
 
@@ -766,7 +980,7 @@ extern "C" int rxb200_fm_process_device(rxb200_fm *h, const int16_t *d_cs16, siz
                                         int16_t *d_pcm, size_t pcm_stride, size_t *n_pcm, int sync)
 {
 	if (!h || !d_cs16 || !d_pcm) { set_error("null argument"); return RXB200_EINVAL; }
-	if (((uintptr_t)d_cs16 & 15u) != 0) { set_error("d_cs16 must be 16-byte aligned"); return RXB200_EINVAL; }
+	if (((uintptr_t)d_cs16 & 31u) != 0) { set_error("d_cs16 must be 32-byte aligned"); return RXB200_EINVAL; }
 	int rc = fm_check_shape(h, n_int16, chunk_int16);
 	if (rc != RXB200_OK) { return rc; }
 	RXB_CUDA(cudaSetDevice(h->device));
@@ -779,7 +993,7 @@ extern "C" int rxb200_fm_process_device(rxb200_fm *h, const int16_t *d_cs16, siz
 	if (n_pcm) { *n_pcm = total; }
 	if (sync) {
 		RXB_CUDA(cudaStreamSynchronize(h->stream));
-		RXB_CUDA(cudaMemcpy(&h->stats.fixup_segments, h->d_fix_count, sizeof(int), cudaMemcpyDeviceToHost));
+		RXB_CUDA(cudaMemcpy(&h->stats.fixup_segments, h->d_sync + 1, sizeof(int), cudaMemcpyDeviceToHost));
 	}
 	return RXB200_OK;
 }
@@ -817,7 +1031,7 @@ extern "C" int rxb200_fm_process(rxb200_fm *h, const int16_t *cs16, size_t n_int
 		RXB_CUDA(cudaMemcpy2DAsync(pcm, pcm_stride * sizeof(int16_t), h->d_out, (total + 8) * sizeof(int16_t),
 		                           total * sizeof(int16_t), (size_t)h->n_channels, cudaMemcpyDeviceToHost, h->stream));
 	}
-	RXB_CUDA(cudaMemcpyAsync(&h->stats.fixup_segments, h->d_fix_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	RXB_CUDA(cudaMemcpyAsync(&h->stats.fixup_segments, h->d_sync + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	RXB_CUDA(cudaStreamSynchronize(h->stream));
 	if (n_pcm) { *n_pcm = total; }
 	return RXB200_OK;
@@ -839,10 +1053,10 @@ extern "C" void *rxb200_fm_stream(rxb200_fm *h) { return h ? (void *)h->stream :
 extern "C" int rxb200_fm_last_stats(rxb200_fm *h, rxb200_fm_stats *out)
 {
 	if (!h || !out) { return RXB200_EINVAL; }
-	if (h->stats.fixup_segments < 0) {
+	if (h->stats.fixup_segments < 0 && h->d_sync) {
 		RXB_CUDA(cudaSetDevice(h->device));
 		RXB_CUDA(cudaStreamSynchronize(h->stream));
-		RXB_CUDA(cudaMemcpy(&h->stats.fixup_segments, h->d_fix_count, sizeof(int), cudaMemcpyDeviceToHost));
+		RXB_CUDA(cudaMemcpy(&h->stats.fixup_segments, h->d_sync + 1, sizeof(int), cudaMemcpyDeviceToHost));
 	}
 	*out = h->stats;
 	return RXB200_OK;

@@ -43,7 +43,7 @@ def test_fm_matches_oracle_and_golden(case, port):
     d.close()
 
 
-@pytest.mark.parametrize("seg", [64, 1024, 4096])
+@pytest.mark.parametrize("seg", [64, 256, 4096])
 @pytest.mark.parametrize("name", ["cfg2B", "cfg2A", "nbfm_D42_lut", "wbfm_default", "F9_P5_lut", "raw_D4", "zeros_deemph",
                                   "burst_then_silence", "fullscale_noise_P3"])
 def test_fm_small_segments(name, seg, port):
