@@ -41,8 +41,26 @@ __host__ __device__ __forceinline__ int div_c(int n, int d)
 // in tests/test_fm_gpu.py).  Result is in [-127, 128].
 __host__ __device__ __forceinline__ int scale_cs16(int x)
 {
+	// t < 0  <=>  x <= -103  <=>  the real value is negative: floor + 1 == truncation toward zero
 	int t = x * 32769 + 3355366;
-	return (t >> 23) + (x < -102 ? 1 : 0);
+	return (t >> 23) - (t >> 31);
 }
+
+#ifdef __CUDACC__
+// C's truncating n / d for d > 0 when |n / d| is small (< 2^20): fp32 estimate (error < 1) and an
+// exact integer remainder check.  Falls back to div_c otherwise.  Bit-exact with '/'.
+__device__ __forceinline__ int div_small_quotient(int n, int d)
+{
+	if (d <= 0) { return div_c(n, d); }
+	int q = __float2int_rz(__int2float_rn(n) * __frcp_rn(__int2float_rn(d)));
+	int r = sub_w(n, mul_w(q, d));           // exact in two's complement whenever |q - n/d| <= 1
+	if (n >= 0) {
+		if (r < 0) { q--; } else if (r >= d) { q++; }
+	} else {
+		if (r > 0) { q++; } else if (r <= -d) { q--; }
+	}
+	return q;
+}
+#endif
 
 }  // namespace rxb

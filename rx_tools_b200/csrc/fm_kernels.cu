@@ -90,7 +90,7 @@ struct FrontState {
 	uint32_t h[PL > 0 ? PL : 1][6];
 	// scalar passes (level >= 3): the reference's window a..f plus the odd sample waiting for its pair
 	int wi[PS > 0 ? PS : 1][6], wq[PS > 0 ? PS : 1][6], pi[PS > 0 ? PS : 1], pq[PS > 0 ? PS : 1];
-	int di[9], dq[9];          // generic_fir history
+	uint32_t fh[9];            // generic_fir history, I low / Q high half-word (raw int16)
 	int pre_i, pre_q;
 };
 
@@ -110,7 +110,7 @@ __device__ __forceinline__ void front_zero(FrontState<P> &s)
 		s.pi[l] = 0; s.pq[l] = 0;
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { s.di[j] = 0; s.dq[j] = 0; }
+	for (int j = 0; j < 9; j++) { s.fh[j] = 0u; }
 	s.pre_i = s.pre_q = 0;
 }
 
@@ -132,7 +132,7 @@ __device__ __forceinline__ void front_load(FrontState<P> &s, const uint32_t *g)
 		uint32_t w = g[ST_HDR + 6 * PL + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * PS + j]; s.di[j] = lo16(w); s.dq[j] = hi16(w); }
+	for (int j = 0; j < 9; j++) { s.fh[j] = g[ST_HDR + 6 * PL + 7 * PS + j]; }
 }
 
 template <int P>
@@ -153,7 +153,7 @@ __device__ __forceinline__ void front_store(const FrontState<P> &s, uint32_t *g)
 		g[ST_HDR + 6 * PL + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = pack2(s.di[j], s.dq[j]); }
+	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = s.fh[j]; }
 }
 
 // ------------------------------------------------------------------------------ stages
@@ -195,18 +195,25 @@ __device__ __forceinline__ bool scalar_push(FrontState<P> &s, int xi, int xq, un
 	}
 }
 
-// generic_fir (src/rtl_fm.c:442-465): output from the previous nine samples, then shift in x.
-__device__ __forceinline__ int droop9(int (&h)[9], const int (&c)[6], int x)
+// generic_fir (src/rtl_fm.c:442-465) on both components: output from the PREVIOUS nine samples, then
+// the current sample is shifted into the history.  int32 wrap-around preserved.
+__device__ __forceinline__ void droop9(uint32_t (&h)[9], const int (&c)[6], int &di, int &dq)
 {
-	int acc = mul_w(h[0] + h[8], c[1]);
-	acc = add_w(acc, mul_w(h[1] + h[7], c[2]));
-	acc = add_w(acc, mul_w(h[2] + h[6], c[3]));
-	acc = add_w(acc, mul_w(h[3] + h[5], c[4]));
-	acc = add_w(acc, mul_w(h[4], c[5]));
+	int ai = mul_w(lo16(h[0]) + lo16(h[8]), c[1]);
+	int aq = mul_w(hi16(h[0]) + hi16(h[8]), c[1]);
+	ai = add_w(ai, mul_w(lo16(h[1]) + lo16(h[7]), c[2]));
+	aq = add_w(aq, mul_w(hi16(h[1]) + hi16(h[7]), c[2]));
+	ai = add_w(ai, mul_w(lo16(h[2]) + lo16(h[6]), c[3]));
+	aq = add_w(aq, mul_w(hi16(h[2]) + hi16(h[6]), c[3]));
+	ai = add_w(ai, mul_w(lo16(h[3]) + lo16(h[5]), c[4]));
+	aq = add_w(aq, mul_w(hi16(h[3]) + hi16(h[5]), c[4]));
+	ai = add_w(ai, mul_w(lo16(h[4]), c[5]));
+	aq = add_w(aq, mul_w(hi16(h[4]), c[5]));
 #pragma unroll
 	for (int j = 0; j < 8; j++) { h[j] = h[j + 1]; }
-	h[8] = x;
-	return wrap16(acc >> 15);
+	h[8] = pack2(di, dq);
+	di = wrap16(ai >> 15);
+	dq = wrap16(aq >> 15);
 }
 
 // polar_discriminant (src/rtl_fm.c:476-483); note 3.14159.
@@ -223,8 +230,10 @@ __device__ __forceinline__ int fast_atan2_i(int y, int x)
 	if (x == 0 && y == 0) { return 0; }
 	int ya = y < 0 ? neg_w(y) : y;
 	int ang;
-	if (x >= 0) { ang = sub_w(q1, div_c(mul_w(q1, sub_w(x, ya)), add_w(x, ya))); }
-	else        { ang = sub_w(q3, div_c(mul_w(q1, add_w(x, ya)), sub_w(ya, x))); }
+	// the quotient is bounded by 4096 in magnitude whenever the divisor is positive (also after
+	// int32 wrap-around of the numerator), so the fp32-estimate division is exact; else C semantics
+	if (x >= 0) { ang = sub_w(q1, div_small_quotient(mul_w(q1, sub_w(x, ya)), add_w(x, ya))); }
+	else        { ang = sub_w(q3, div_small_quotient(mul_w(q1, add_w(x, ya)), sub_w(ya, x))); }
 	return y < 0 ? neg_w(ang) : ang;
 }
 
@@ -284,53 +293,62 @@ __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int
 // (thread stride ~ Sf/D entries) nor the back-end loads (lane stride = piece) pile on one bank
 __device__ __forceinline__ int pcm_phys(int rel) { return rel + 2 * (rel >> 7); }
 
+// Compile-time specialisation of the flags that sit in the per-sample path.  SPEC 0: everything is a
+// (warp-uniform) run-time branch.  SPEC 1: the wbfm shape — FM discriminator with fast_atan2, fs/4
+// rotation on, serial stages present — resolved at compile time.
+template <int SPEC>
+struct Spec {
+	static __device__ __forceinline__ int mode(const FmDev &c) { return SPEC == 1 ? RXB200_MODE_FM : c.mode; }
+	static __device__ __forceinline__ int atan_mode(const FmDev &c) { return SPEC == 1 ? RXB200_ATAN_FAST : c.atan_mode; }
+	static __device__ __forceinline__ bool rotate(const FmDev &c) { return SPEC == 1 ? true : !c.offset_tuning; }
+	static __device__ __forceinline__ bool direct(const FmCall &k) { return SPEC == 1 ? false : (k.direct_out != 0); }
+};
+
 struct EmitCtx {
 	int16_t *pcm;            // shared PCM buffer
 	int16_t *out;            // channel output (direct_out only)
-	long long m;             // decimated index of the next sample
 	long long m_lo;          // decimated index of pcm[0]
+	int rel;                 // decimated index of the next sample, relative to m_lo
 	int first_in_chunk;
-	bool store;              // emission belongs to this thread's own segment
 };
 
-// Everything between the decimator and the serial stages, for one decimated sample.
-template <int P>
+// Everything between the decimator and the serial stages, for one decimated sample.  STORE: the
+// sample belongs to this thread's own segment (otherwise it only advances the filter state).
+template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e, int di, int dq)
 {
-	if (c.fir_on) {
-		di = droop9(s.di, c.fir, di);
-		dq = droop9(s.dq, c.fir, dq);
-	}
+	if (c.fir_on) { droop9(s.fh, c.fir, di, dq); }
+	const int mode = Spec<SPEC>::mode(c);
 	int pcm;
-	if (c.mode == RXB200_MODE_FM) {
+	if (mode == RXB200_MODE_FM) {
+		const int am = Spec<SPEC>::atan_mode(c);
 		int br = s.pre_i, bj = s.pre_q;
 		int cr = add_w(mul_w(di, br), mul_w(dq, bj));       // x[n] * conj(x[n-1]) (src/rtl_fm.c:470-474)
 		int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
-		if (e.first_in_chunk || c.atan_mode == RXB200_ATAN_STD) { pcm = disc_std(cr, cj); }   // F8
-		else if (c.atan_mode == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
-		else if (c.atan_mode == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }
+		if (e.first_in_chunk || am == RXB200_ATAN_STD) { pcm = disc_std(cr, cj); }   // F8
+		else if (am == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
+		else if (am == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }
 		else { pcm = disc_ale(di, dq, br, bj); }
-		pcm = wrap16(pcm);
 		s.pre_i = di; s.pre_q = dq;
-	} else if (c.mode == RXB200_MODE_AM) {
+	} else if (mode == RXB200_MODE_AM) {
 		int en = add_w(mul_w(di, di), mul_w(dq, dq));
-		pcm = wrap16(mul_w(wrap16((int)sqrt((double)en)), c.out_scale));
-	} else if (c.mode == RXB200_MODE_USB) {
-		pcm = wrap16(mul_w(wrap16(di + dq), c.out_scale));
-	} else if (c.mode == RXB200_MODE_LSB) {
-		pcm = wrap16(mul_w(wrap16(di - dq), c.out_scale));
+		pcm = mul_w(wrap16((int)sqrt((double)en)), c.out_scale);
+	} else if (mode == RXB200_MODE_USB) {
+		pcm = mul_w(wrap16(di + dq), c.out_scale);
+	} else if (mode == RXB200_MODE_LSB) {
+		pcm = mul_w(wrap16(di - dq), c.out_scale);
 	} else {   // raw: lowpassed copied out, nothing after (src/rtl_fm.c:658-665, :809-811)
-		if (e.store) { e.out[2 * e.m] = (int16_t)di; e.out[2 * e.m + 1] = (int16_t)dq; }
-		e.m++;
+		if (STORE) { long long m = e.m_lo + e.rel; e.out[2 * m] = (int16_t)di; e.out[2 * m + 1] = (int16_t)dq; }
+		e.rel++;
 		e.first_in_chunk = 0;
 		return;
 	}
 	e.first_in_chunk = 0;
-	if (e.store) {
-		if (k.direct_out) { e.out[e.m] = (int16_t)pcm; }
-		else { e.pcm[pcm_phys((int)(e.m - e.m_lo))] = (int16_t)pcm; }
+	if (STORE) {      // the int16 store is the reference's (int16_t) cast
+		if (Spec<SPEC>::direct(k)) { e.out[e.m_lo + e.rel] = (int16_t)pcm; }
+		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
 	}
-	e.m++;
+	e.rel++;
 }
 
 // scale + fs/4 rotation of one CS16 word (I low, Q high): rotate16_90 multiplies sample n of the chunk by
@@ -361,12 +379,12 @@ __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
 }
 
 // One block of 8 input samples at in-chunk offset u (multiple of 8).
-template <int P>
+template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
                                             const uint32_t (&v)[8], unsigned u)
 {
 	constexpr int PL = FrontState<P>::PL;
-	const bool rot = !c.offset_tuning;
+	const bool rot = Spec<SPEC>::rotate(c);
 	if constexpr (P == 0) {
 		// low_pass boxcar (src/rtl_fm.c:351-371)
 #pragma unroll
@@ -377,7 +395,7 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 			if (++s.box_n >= c.D) {
 				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
 				s.box_i = 0; s.box_q = 0; s.box_n = 0;
-				post_decim<P>(c, k, s, e, di, dq);
+				post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
 			}
 		}
 	} else {
@@ -421,9 +439,9 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 				if constexpr (P > PL) {
 					// in-chunk index of this sample at pass PL: (u >> PL) + j
 					int oi, oq;
-					if (scalar_push<0, P>(s, di, dq, (u >> PL) + (unsigned)j, oi, oq)) { post_decim<P>(c, k, s, e, oi, oq); }
+					if (scalar_push<0, P>(s, di, dq, (u >> PL) + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
 				} else {
-					post_decim<P>(c, k, s, e, di, dq);
+					post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
 				}
 			}
 		}
@@ -431,40 +449,76 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 }
 
 // ------------------------------------------------------------------------------ back end
-struct BackState { int lo, hi, acc, phase, dirty; };
-
-// One PCM sample through deemph + low_pass_real; returns true when the bracket is open.
-__device__ __forceinline__ void back_step(const FmDev &c, BackState &b, int pcm, bool valid, bool emit,
-                                          int16_t *__restrict__ out, long long &oidx)
+// First PCM index (counted from the start of the call) of the group low_pass_real sums into output o:
+// the resampler adds `slow` per sample and emits when the running phase reaches `fast`
+// (src/rtl_fm.c:396-407), so output o-1 is emitted by the first sample m with
+// phase0 + (m+1)*slow >= o*fast.
+__device__ __forceinline__ long long group_start(const FmDev &c, long long o, int phase0)
 {
-	bool inexact = !valid;
-	if (c.deemph) {
-		bool same = (b.lo == b.hi);
-		b.lo = deemph_step(c, b.lo, pcm);
-		b.hi = same ? b.lo : deemph_step(c, b.hi, pcm);
-		pcm = wrap16(b.lo);
-		inexact = inexact || (b.lo != b.hi);
-	}
-	if (c.resample) {     // low_pass_real (src/rtl_fm.c:389-409)
-		if (inexact) { b.dirty = 1; }
-		b.acc = add_w(b.acc, pcm);
-		b.phase += c.slow;
-		if (b.phase >= c.fast) {
-			if (emit) { out[oidx] = (int16_t)(b.acc / c.lpr_div); }
-			oidx++;
-			b.phase -= c.fast;
-			b.acc = 0;
-			b.dirty = 0;
-		}
-	} else {
-		b.dirty = inexact ? 1 : 0;
-		if (emit) { out[oidx] = (int16_t)pcm; }
-		oidx++;
+	if (!c.resample) { return o; }
+	if (o <= 0) { return 0; }
+	long long need = o * (long long)c.fast - (long long)phase0;
+	return (need + c.slow - 1) / c.slow;
+}
+
+// deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a piece).
+__device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
+{
+#pragma unroll 4
+	for (; m < m_end; m++) {
+		int x = (int)pcm_s[pcm_phys(m)];
+		lo = deemph_step(c, lo, x);
+		hi = deemph_step(c, hi, x);
 	}
 }
 
-template <int P>
-__global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, const FmCall k)
+// Outputs [oa, ob) of one lane from an exact state: per output, de-emphasise the group's samples,
+// sum them and divide by the integer rate ratio (deemph_filter :673-680, low_pass_real :396-407).
+// Returns the state after the last group; m is the running (buffer-relative) PCM index.
+__device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out,
+                                             long long oa, long long ob, int &m, int &avg, int acc, int phase)
+{
+	for (long long o = oa; o < ob; o++) {
+		int len = 1;
+		if (c.resample) {
+			len = (c.fast - phase + c.slow - 1) / c.slow;
+			phase += len * c.slow - c.fast;
+		}
+		for (int j = 0; j < len; j++) {
+			int x = (int)pcm_s[pcm_phys(m++)];
+			if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
+			acc = add_w(acc, x);
+		}
+		out[o] = (int16_t)(c.resample ? div_small_quotient(acc, c.lpr_div) : acc);
+		acc = 0;
+	}
+}
+
+// Runs blocks [t, t_end) of one segment; chunk bookkeeping shared by the replay and the owned part.
+template <int P, int SPEC, bool STORE>
+__device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
+                                          const int16_t *__restrict__ in, int t, int t_end, unsigned &u)
+{
+	for (; t < t_end; t += 8) {
+		if (u >= (unsigned)k.chunk) { u = 0u; }
+		if (u == 0u) {
+			e.first_in_chunk = 1;
+			// chunk start: every pass forgets the odd sample it was holding
+#pragma unroll
+			for (int l = 0; l < FrontState<P>::PL; l++) {
+#pragma unroll
+				for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
+			}
+		}
+		uint32_t v[8];
+		ldg256(in + 2 * (size_t)t, v);
+		front_block<P, SPEC, STORE>(c, k, s, e, v, u);
+		u += 8u;
+	}
+}
+
+template <int P, int SPEC>
+__global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
@@ -481,7 +535,6 @@ __global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, 
 		const uint32_t *carry = k.carry_in + (size_t)ch * k.state_words;
 		const int box_n0 = (int)carry[ST_BOX_N];
 		const int phase0 = (int)carry[ST_LPR_PHASE];
-		const int16_t *__restrict__ in = k.in + 2 * (size_t)ch * (size_t)k.n;
 		int16_t *__restrict__ out = k.out + (size_t)ch * (size_t)k.out_stride;
 		const long long own_lo = (long long)b * k.n_own * k.Sf;
 		long long own_hi = own_lo + (long long)k.n_own * k.Sf;
@@ -489,15 +542,15 @@ __global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, 
 		long long buf_lo = own_lo - (long long)k.n_extra * k.Sf;
 		if (buf_lo < 0) { buf_lo = 0; }
 		const long long m_lo = dec_before(c, buf_lo, box_n0);
-		const long long m_own = dec_before(c, own_lo, box_n0);
-		const long long m_hi = dec_before(c, own_hi, box_n0);
+		const int m_own = (int)(dec_before(c, own_lo, box_n0) - m_lo);     // relative to m_lo from here on
+		const int m_hi = (int)(dec_before(c, own_hi, box_n0) - m_lo);
 
 		// ---------------- front end: one segment per thread
 		{
 			const long long g = (long long)b * k.n_own + (tid - k.n_extra);
 			const long long start = g * k.Sf;
 			if (g >= 0 && start < k.n) {
-				long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
+				const long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
 				long long t0 = start - k.halo;
 				FrontState<P> s;
 				if (t0 <= 0) { t0 = 0; front_load<P>(s, carry); }
@@ -506,36 +559,23 @@ __global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, 
 					if (P == 0) { s.box_n = (int)((t0 + box_n0) % c.D); }
 				}
 				unsigned u = (unsigned)(t0 % k.chunk);
+				const long long m0 = dec_before(c, t0, box_n0);
 				EmitCtx e;
 				e.pcm = pcm_s; e.out = out; e.m_lo = m_lo;
-				e.m = dec_before(c, t0, box_n0);
+				e.rel = (int)(m0 - m_lo);
 				e.first_in_chunk = 0;
-				if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, box_n0) == e.m) ? 1 : 0; }
-				e.store = false;
-				for (long long t = t0; t < end; t += 8) {
-					if (u >= (unsigned)k.chunk) { u = 0u; }
-					if (u == 0u) {
-						e.first_in_chunk = 1;
-						// chunk start: every pass forgets the odd sample it was holding
-#pragma unroll
-						for (int l = 0; l < FrontState<P>::PL; l++) {
-#pragma unroll
-							for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
-						}
-					}
-					if (t >= start) { e.store = true; }
-					uint32_t v[8];
-					ldg256(in + 2 * t, v);
-					front_block<P>(c, k, s, e, v, u);
-					u += 8u;
-				}
+				if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, box_n0) == m0) ? 1 : 0; }
+				// offsets relative to t0 fit 32 bits (a segment plus its halo)
+				const int16_t *__restrict__ in = k.in + 2 * ((size_t)ch * (size_t)k.n + (size_t)t0);
+				front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), u);
+				front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), u);
 				if (end == k.n) {
 					// this thread saw the end of the stream: its registers are the next call's carry
 					front_store<P>(s, k.carry_out + (size_t)ch * k.state_words);
 				}
 			}
 		}
-		if (k.direct_out) {
+		if (Spec<SPEC>::direct(k)) {
 			if (tid == 0 && b == k.n_cta - 1) {
 				uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
 				co[ST_AVG] = carry[ST_AVG]; co[ST_LPR_ACC] = carry[ST_LPR_ACC]; co[ST_LPR_PHASE] = carry[ST_LPR_PHASE];
@@ -545,101 +585,90 @@ __global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, 
 		}
 		__syncthreads();
 
-		// ---------------- back end: warp 0, one contiguous piece of the CTA's PCM per lane
+		// ---------------- back end: warp 0, one contiguous run of OUTPUTS per lane.  Pieces start on
+		// resampler group boundaries, so the only state a piece inherits is the de-emphasis average.
 		if (tid < 32) {
 			const int lane = tid;
-			const long long count = m_hi - m_own;
-			long long piece = (count + 31) / 32;
-			piece += (2 - (piece & 3) + 4) & 3;          // piece = 2 (mod 4): lane stride is an odd number of words
-			if (piece < 2) { piece = 2; }
-			const long long p0 = m_own + (long long)lane * piece;
-			long long p1 = p0 + piece;
-			if (p1 > m_hi) { p1 = m_hi; }
-			const bool active = p0 < m_hi;
-			const int last_lane = count > 0 ? (int)((count - 1) / piece) : 0;
-			BackState bs;
-			bs.lo = -32768; bs.hi = 32767; bs.acc = 0; bs.phase = 0; bs.dirty = 1;
-			long long oidx = 0;
+			const bool last_cta = (b == k.n_cta - 1);
+			const long long o_first = out_before(c, m_lo + m_own, phase0);
+			const long long o_end = out_before(c, m_lo + m_hi, phase0);
+			const int n_out = (int)(o_end - o_first);
+			int per = (n_out + 31) / 32;
+			if (per < 1) { per = 1; }
+			long long oa = o_first + (long long)lane * per;
+			long long ob = oa + per;
+			if (oa > o_end) { oa = o_end; }
+			if (ob > o_end) { ob = o_end; }
+			const bool active = oa < ob;
+			const int last_lane = n_out > 0 ? (n_out - 1) / per : 0;
+			const int ga = (int)(group_start(c, oa, phase0) - m_lo);        // buffer-relative PCM indices
+			int lo = -32768, hi = 32767;
+			int avg = 0, m_run = ga;
 			bool start_ok = true;
-			if (active) {
-				long long ms = p0 - k.W_dec;
-				if (ms < m_lo) { ms = m_lo; }
-				const bool exact = (ms == 0);                 // start of the call: the carry is the state
-				if (exact) { bs.lo = bs.hi = (int)carry[ST_AVG]; bs.acc = (int)carry[ST_LPR_ACC]; bs.dirty = 0; }
-				if (!c.deemph) { bs.lo = bs.hi = 0; }
-				if (c.resample) { bs.phase = (int)(((long long)phase0 + ms * (long long)c.slow) % (long long)c.fast); }
-				oidx = out_before(c, ms, phase0);
-				for (long long m = ms; m < p0; m++) {
-					back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, false, out, oidx);
-				}
-				start_ok = exact || (!bs.dirty && bs.lo == bs.hi);
-				for (long long m = p0; m < p1; m++) {
-					back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, true, out, oidx);
-				}
+			const bool at_origin = (m_lo == 0 && ga == 0);                  // stream start: carry is the state
+			if (active || lane == 0) {
+				int ws = ga - k.W_dec;
+				if (ws < 0) { ws = 0; }
+				if (m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
+				if (c.deemph) { back_replay(c, pcm_s, ws, ga, lo, hi); }
+				start_ok = !c.deemph || (lo == hi);
+				if (b == 0 && lane == 0) { start_ok = true; }
+				avg = lo;
 			}
-			// resolve lanes whose bracket was still open at their piece start
-			bool need = active && !start_ok;
-			bool end_exact = !active || start_ok || (!bs.dirty && bs.lo == bs.hi);
-			int pred_avg = 0, pred_acc = 0;
-			bool have_pred = false;
+			const int acc0 = at_origin ? (int)carry[ST_LPR_ACC] : 0;
+			const int ph0 = c.resample ? (int)(((long long)phase0 + (m_lo + ga) * (long long)c.slow - oa * (long long)c.fast)) : 0;
+			if (active && start_ok) { back_outputs(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+			// lanes whose bracket was still open take their left neighbour's end state, left to right
+			bool need = (active || lane == 0) && !start_ok;
+			bool end_exact = !need;
+			int pred_avg = 0;
 			for (int round = 0; round < 34; round++) {
 				unsigned need_mask = __ballot_sync(0xffffffffu, need);
 				if (need_mask == 0u) { break; }
-				int up_avg = __shfl_up_sync(0xffffffffu, bs.lo, 1);
-				int up_acc = __shfl_up_sync(0xffffffffu, bs.acc, 1);
+				int up_avg = __shfl_up_sync(0xffffffffu, avg, 1);
 				int up_ok = __shfl_up_sync(0xffffffffu, end_exact ? 1 : 0, 1);
 				bool can = false;
 				if (need) {
 					if (lane == 0) {
 						// left neighbour is the previous CTA of this channel (older ticket): wait for its end state
-						if (!have_pred) {
-							volatile int *pp = k.pub + 4 * (size_t)(work - 1);
-							while (pp[0] == 0) { __nanosleep(64); }
-							__threadfence();
-							pred_avg = pp[1]; pred_acc = pp[2];
-							have_pred = true;
-						}
+						volatile int *pp = k.pub + 4 * (size_t)(work - 1);
+						while (pp[0] == 0) { __nanosleep(64); }
+						__threadfence();
+						pred_avg = pp[1];
 						can = true;
 					} else if (up_ok) {
-						pred_avg = up_avg; pred_acc = up_acc;
+						pred_avg = up_avg;
 						can = true;
 					}
 				}
 				if (can) {
-					bs.lo = bs.hi = c.deemph ? pred_avg : 0;
-					bs.acc = pred_acc; bs.dirty = 0;
-					if (c.resample) { bs.phase = (int)(((long long)phase0 + p0 * (long long)c.slow) % (long long)c.fast); }
-					oidx = out_before(c, p0, phase0);
-					for (long long m = p0; m < p1; m++) {
-						back_step(c, bs, (int)pcm_s[pcm_phys((int)(m - m_lo))], true, true, out, oidx);
-					}
+					avg = pred_avg; m_run = ga;
+					if (active) { back_outputs(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
 					need = false; end_exact = true;
 					atomicAdd(k.fix_count, 1);
 				}
 			}
-			// publish this CTA's end state for its right neighbour; the last CTA writes the carry
-			int fin_avg = __shfl_sync(0xffffffffu, bs.lo, last_lane);
-			int fin_acc = __shfl_sync(0xffffffffu, bs.acc, last_lane);
-			int fin_phase = __shfl_sync(0xffffffffu, bs.phase, last_lane);
+			// end state of the CTA = state of its last active lane (lane 0 when it produced nothing)
+			int fin_avg = __shfl_sync(0xffffffffu, avg, last_lane);
+			int fin_m = __shfl_sync(0xffffffffu, m_run, last_lane);
 			if (lane == 0) {
-				if (count <= 0) {
-					// nothing decimated in this stretch: hand the neighbour's state through
-					if (b == 0) { fin_avg = (int)carry[ST_AVG]; fin_acc = (int)carry[ST_LPR_ACC]; }
-					else {
-						volatile int *pp = k.pub + 4 * (size_t)(work - 1);
-						while (pp[0] == 0) { __nanosleep(64); }
-						__threadfence();
-						fin_avg = pp[1]; fin_acc = pp[2];
+				if (!last_cta) {
+					volatile int *mp = k.pub + 4 * (size_t)work;
+					mp[1] = fin_avg;
+					__threadfence();
+					mp[0] = 1;
+				} else {
+					// tail of the stream: samples after the last emitted output stay in the accumulator
+					int acc = (m_lo == 0 && fin_m == 0) ? (int)carry[ST_LPR_ACC] : 0;
+					for (int m = fin_m; m < m_hi; m++) {
+						int x = (int)pcm_s[pcm_phys(m)];
+						if (c.deemph) { fin_avg = deemph_step(c, fin_avg, x); x = wrap16(fin_avg); }
+						acc = add_w(acc, x);
 					}
-					fin_phase = c.resample ? (int)(((long long)phase0 + m_hi * (long long)c.slow) % (long long)c.fast) : 0;
-				}
-				volatile int *mp = k.pub + 4 * (size_t)work;
-				mp[1] = fin_avg; mp[2] = fin_acc;
-				__threadfence();
-				mp[0] = 1;
-				if (b == k.n_cta - 1) {
 					uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
-					co[ST_AVG] = (uint32_t)fin_avg; co[ST_LPR_ACC] = (uint32_t)fin_acc; co[ST_LPR_PHASE] = (uint32_t)fin_phase;
+					co[ST_AVG] = (uint32_t)fin_avg;
+					co[ST_LPR_ACC] = (uint32_t)(c.resample ? acc : 0);
+					co[ST_LPR_PHASE] = c.resample ? (uint32_t)(((long long)phase0 + (m_lo + m_hi) * (long long)c.slow) % (long long)c.fast) : 0u;
 					co[ST_SQ_HITS] = carry[ST_SQ_HITS];
 				}
 			}
@@ -648,20 +677,30 @@ __global__ void __launch_bounds__(FM_THREADS, 2) fm_fused_kernel(const FmDev c, 
 }
 
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
-static fm_kernel_fn pick_kernel(int P)
+static fm_kernel_fn pick_kernel(int P, int spec)
 {
+	if (spec == 1) {
+		switch (P) {
+		case 0: return fm_fused_kernel<0, 1>;
+		case 1: return fm_fused_kernel<1, 1>;
+		case 2: return fm_fused_kernel<2, 1>;
+		case 3: return fm_fused_kernel<3, 1>;
+		case 4: return fm_fused_kernel<4, 1>;
+		default: break;
+		}
+	}
 	switch (P) {
-	case 0: return fm_fused_kernel<0>;
-	case 1: return fm_fused_kernel<1>;
-	case 2: return fm_fused_kernel<2>;
-	case 3: return fm_fused_kernel<3>;
-	case 4: return fm_fused_kernel<4>;
-	case 5: return fm_fused_kernel<5>;
-	case 6: return fm_fused_kernel<6>;
-	case 7: return fm_fused_kernel<7>;
-	case 8: return fm_fused_kernel<8>;
-	case 9: return fm_fused_kernel<9>;
-	case 10: return fm_fused_kernel<10>;
+	case 0: return fm_fused_kernel<0, 0>;
+	case 1: return fm_fused_kernel<1, 0>;
+	case 2: return fm_fused_kernel<2, 0>;
+	case 3: return fm_fused_kernel<3, 0>;
+	case 4: return fm_fused_kernel<4, 0>;
+	case 5: return fm_fused_kernel<5, 0>;
+	case 6: return fm_fused_kernel<6, 0>;
+	case 7: return fm_fused_kernel<7, 0>;
+	case 8: return fm_fused_kernel<8, 0>;
+	case 9: return fm_fused_kernel<9, 0>;
+	case 10: return fm_fused_kernel<10, 0>;
 	default: return nullptr;
 	}
 }
@@ -773,7 +812,13 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	memset(h, 0, sizeof *h);
 	h->p = *params; h->device = device; h->n_channels = n_channels;
 	h->state_words = fm_state_words(params->downsample_passes);
-	h->kern = pick_kernel(params->downsample_passes);
+	{
+		// wbfm shape: FM + fast_atan2 + rotation, with a serial stage (de-emphasis or resampler)
+		const bool serial = (params->deemph != 0) || (params->rate_out2 > 0);
+		const int spec = (params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
+		                  !params->offset_tuning && serial) ? 1 : 0;
+		h->kern = pick_kernel(params->downsample_passes, spec);
+	}
 	cudaDeviceProp prop;
 	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
 	h->n_sm = prop.multiProcessorCount;
@@ -909,8 +954,10 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample)) ? 1 : 0;
 	// back-end replay (decimated samples): de-emphasis bracket + one resampler group
 	long long wd = 0;
-	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
-	const long long W_dec = direct_out ? 0 : wd + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
+	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 14LL * p.deemph_a + 32; }
+	const long long W_dec = direct_out ? 0 : wd;
+	// PCM the CTA needs from before its stretch: the replay plus the resampler group in progress
+	const long long margin_dec = direct_out ? 0 : W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
 	// segment per thread: ~128 decimated samples, at least 4 halos, capped so the PCM buffer stays small
 	long long Sf = h->tune_seg;
 	if (Sf <= 0) { const char *e = getenv("RXB200_FM_SEG"); Sf = e ? atoll(e) : 0; }
@@ -923,7 +970,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	long long n_extra, n_own, stretch, n_cta, ppt, pcm_cap;
 	size_t smem;
 	for (;;) {
-		n_extra = direct_out ? 0 : ((W_dec + 2) * Dtot + halo + Sf - 1) / Sf;
+		n_extra = direct_out ? 0 : (margin_dec * Dtot + halo + Sf - 1) / Sf;
 		ppt = Sf / Dtot + 2;
 		pcm_cap = direct_out ? 8 : (long long)FM_THREADS * ppt + 64;
 		pcm_cap += 2 * (pcm_cap >> 7) + 8;
@@ -934,12 +981,12 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		}
 		if ((long long)smem > h->smem_optin && Sf > G) {
 			Sf = round_up_ll(Sf / 2, G);          // PCM buffer too large: shorten the segments
-			if (((W_dec + 2) * Dtot + halo + Sf - 1) / Sf <= FM_THREADS / 2) { continue; }
+			if ((margin_dec * Dtot + halo + Sf - 1) / Sf <= FM_THREADS / 2) { continue; }
 		}
 		break;
 	}
 	if ((long long)smem > h->smem_optin || n_extra >= FM_THREADS) {
-		set_error("no segment length fits: warm-up %lld samples, D=%lld, shared memory %d", (W_dec + 2) * Dtot, Dtot, h->smem_optin);
+		set_error("no segment length fits: warm-up %lld samples, D=%lld, shared memory %d", margin_dec * Dtot, Dtot, h->smem_optin);
 		return RXB200_EUNSUPPORTED;
 	}
 	n_own = FM_THREADS - n_extra;
