@@ -461,33 +461,73 @@ __device__ __forceinline__ long long group_start(const FmDev &c, long long o, in
 	return (need + c.slow - 1) / c.slow;
 }
 
-// deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a piece).
+// deemph_filter step on the magic-reciprocal path with the loop-invariant part folded into xb:
+//   xb = x + a/2 + K*a;   avg' = avg + umulhi(xb - avg - [a even && x <= avg], magic) - K
+template <bool EVEN>
+__device__ __forceinline__ int deemph_fast(int avg, int x, int xb, unsigned magic, int K)
+{
+	int n = xb - avg;
+	if (EVEN) { n -= (x <= avg) ? 1 : 0; }
+	return avg + (int)__umulhi((unsigned)n, magic) - K;
+}
+
+__device__ __forceinline__ int pcm_load(const int16_t *pcm_s, int m) { return (int)pcm_s[pcm_phys(m)]; }
+
+// deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a
+// piece).  The two trajectories are independent, the next sample is fetched one step ahead.
+template <bool EVEN>
 __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
 {
+	if (m >= m_end) { return; }
+	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
+	const unsigned magic = c.a_magic;
+	int x = pcm_load(pcm_s, m);
+	if (c.a_use_magic) {
 #pragma unroll 4
-	for (; m < m_end; m++) {
-		int x = (int)pcm_s[pcm_phys(m)];
-		lo = deemph_step(c, lo, x);
-		hi = deemph_step(c, hi, x);
+		for (; m < m_end; m++) {
+			int xn = pcm_load(pcm_s, m + 1 < m_end ? m + 1 : m);
+			int xb = x + bias;
+			lo = deemph_fast<EVEN>(lo, x, xb, magic, K);
+			hi = deemph_fast<EVEN>(hi, x, xb, magic, K);
+			x = xn;
+		}
+	} else {
+		for (; m < m_end; m++) {
+			x = pcm_load(pcm_s, m);
+			lo = deemph_step(c, lo, x);
+			hi = deemph_step(c, hi, x);
+		}
 	}
 }
 
 // Outputs [oa, ob) of one lane from an exact state: per output, de-emphasise the group's samples,
 // sum them and divide by the integer rate ratio (deemph_filter :673-680, low_pass_real :396-407).
-// Returns the state after the last group; m is the running (buffer-relative) PCM index.
+// `phase` is the resampler phase at the first group's start; right after an emission it is < slow, so a
+// group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
+// group a call inherits from the previous call can start with a larger phase).
+// m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
+template <bool EVEN>
 __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out,
                                              long long oa, long long ob, int &m, int &avg, int acc, int phase)
 {
+	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
+	const unsigned magic = c.a_magic;
+	const int lf = c.resample ? c.fast / c.slow : 1;
+	const bool fast_path = c.deemph && c.a_use_magic;
+	int x = (oa < ob) ? pcm_load(pcm_s, m) : 0;
 	for (long long o = oa; o < ob; o++) {
 		int len = 1;
 		if (c.resample) {
-			len = (c.fast - phase + c.slow - 1) / c.slow;
+			if (phase >= c.slow) { len = (c.fast - phase + c.slow - 1) / c.slow; }   // first group of a call only
+			else { len = lf; if (phase + len * c.slow < c.fast) { len++; } }
 			phase += len * c.slow - c.fast;
 		}
 		for (int j = 0; j < len; j++) {
-			int x = (int)pcm_s[pcm_phys(m++)];
-			if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
+			int xn = pcm_load(pcm_s, m + 1);      // one entry of slack exists past the last sample
+			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, x + bias, magic, K); x = wrap16(avg); }
+			else if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
 			acc = add_w(acc, x);
+			x = xn; m++;
 		}
 		out[o] = (int16_t)(c.resample ? div_small_quotient(acc, c.lpr_div) : acc);
 		acc = 0;
@@ -497,9 +537,15 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 // Runs blocks [t, t_end) of one segment; chunk bookkeeping shared by the replay and the owned part.
 template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
-                                          const int16_t *__restrict__ in, int t, int t_end, unsigned &u)
+                                          const int16_t *__restrict__ in, int t, int t_end, int t_last, unsigned &u)
 {
+	if (t >= t_end) { return; }
+	uint32_t v[8], vn[8];
+	ldg256(in + 2 * (size_t)t, v);
 	for (; t < t_end; t += 8) {
+		// fetch the next block (clamped to the segment's last block) while this one is processed
+		const int tn = t + 8 <= t_last ? t + 8 : t_last;
+		ldg256(in + 2 * (size_t)tn, vn);
 		if (u >= (unsigned)k.chunk) { u = 0u; }
 		if (u == 0u) {
 			e.first_in_chunk = 1;
@@ -510,10 +556,10 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 				for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
 			}
 		}
-		uint32_t v[8];
-		ldg256(in + 2 * (size_t)t, v);
 		front_block<P, SPEC, STORE>(c, k, s, e, v, u);
 		u += 8u;
+#pragma unroll
+		for (int j = 0; j < 8; j++) { v[j] = vn[j]; }
 	}
 }
 
@@ -567,8 +613,9 @@ __global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) f
 				if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, box_n0) == m0) ? 1 : 0; }
 				// offsets relative to t0 fit 32 bits (a segment plus its halo)
 				const int16_t *__restrict__ in = k.in + 2 * ((size_t)ch * (size_t)k.n + (size_t)t0);
-				front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), u);
-				front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), u);
+				const int t_last = (int)(end - t0) - 8;
+				front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u);
+				front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u);
 				if (end == k.n) {
 					// this thread saw the end of the stream: its registers are the next call's carry
 					front_store<P>(s, k.carry_out + (size_t)ch * k.state_words);
@@ -610,14 +657,19 @@ __global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) f
 				int ws = ga - k.W_dec;
 				if (ws < 0) { ws = 0; }
 				if (m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
-				if (c.deemph) { back_replay(c, pcm_s, ws, ga, lo, hi); }
+				if (c.deemph) {
+					if (c.a_even) { back_replay<true>(c, pcm_s, ws, ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, ga, lo, hi); }
+				}
 				start_ok = !c.deemph || (lo == hi);
 				if (b == 0 && lane == 0) { start_ok = true; }
 				avg = lo;
 			}
 			const int acc0 = at_origin ? (int)carry[ST_LPR_ACC] : 0;
 			const int ph0 = c.resample ? (int)(((long long)phase0 + (m_lo + ga) * (long long)c.slow - oa * (long long)c.fast)) : 0;
-			if (active && start_ok) { back_outputs(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+			if (active && start_ok) {
+				if (c.a_even) { back_outputs<true>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+				else { back_outputs<false>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+			}
 			// lanes whose bracket was still open take their left neighbour's end state, left to right
 			bool need = (active || lane == 0) && !start_ok;
 			bool end_exact = !need;
@@ -643,7 +695,10 @@ __global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) f
 				}
 				if (can) {
 					avg = pred_avg; m_run = ga;
-					if (active) { back_outputs(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+					if (active) {
+						if (c.a_even) { back_outputs<true>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+						else { back_outputs<false>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
+					}
 					need = false; end_exact = true;
 					atomicAdd(k.fix_count, 1);
 				}
@@ -954,7 +1009,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample)) ? 1 : 0;
 	// back-end replay (decimated samples): de-emphasis bracket + one resampler group
 	long long wd = 0;
-	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 14LL * p.deemph_a + 32; }
+	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
 	const long long W_dec = direct_out ? 0 : wd;
 	// PCM the CTA needs from before its stretch: the replay plus the resampler group in progress
 	const long long margin_dec = direct_out ? 0 : W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
