@@ -305,8 +305,9 @@ def run_power(args, rank, local, world):
         wl = "rx_power -f 24M:1766M:1k -c 28.5% -w hamming, 4096-bin fix_fft, 871 hops batched"
     n_hops = plan.n_hops
     # shard hops contiguously over ranks; pad to equal rows for the all-gather
-    per = -(-n_hops // world)
-    hb, he = min(rank * per, n_hops), min((rank + 1) * per, n_hops)
+    from rx_tools_b200 import sharding
+    per = sharding.rows_per_rank(n_hops, world)
+    hb, he = sharding.unit_range(rank, world, n_hops)
     if n_hops == 1:
         hb, he = 0, 1      # one hop: every rank takes a slice of the passes instead
         my_pass = n_pass // world
@@ -320,20 +321,16 @@ def run_power(args, rank, local, world):
     sc = power.PowerScanner(plan, window, device=local)
     stream = torch.cuda.ExternalStream(sc.stream, device=dev)
     N = 1 << plan.bin_e
-    gathered = torch.empty(world * per * N, dtype=torch.int64, device=dev) if world > 1 and n_hops > 1 else None
-
-    send = torch.zeros(per * N, dtype=torch.int64, device=dev) if gathered is not None else None
-    src = _device_view(sc.device_avg_ptr + hb * N * 8, max(nh, 1) * N, dev) if gathered is not None else None
+    do_gather = world > 1 and n_hops > 1
+    src = _device_view(sc.device_avg_ptr + hb * N * 8, max(nh, 1) * N, dev) if do_gather else None
+    gathered = [None]
 
     def step():
         if nh > 0:
             sc.scanner_device(d_in.data_ptr(), my_pass, hb, he, sync=False)
-        if gathered is not None:
-            import torch.distributed as dist
+        if do_gather:
             with torch.cuda.stream(stream):      # ordered after the kernel on the handle's stream
-                if nh > 0:
-                    send[: nh * N].copy_(src[: nh * N])
-                dist.all_gather_into_tensor(gathered, send)
+                gathered[0] = sharding.gather_rows(src[: nh * N] if nh > 0 else src[:0], n_hops, N, world)
 
     for _ in range(args.warmup):
         step()
