@@ -61,6 +61,7 @@ struct FmCall {
 	int W_dec;                // back-end replay length (decimated samples)
 	int pcm_cap;              // int16 entries of the shared PCM buffer
 	int direct_out;           // 1: no serial stage, the front end stores the output itself
+	int be_lanes;             // threads of the CTA that run the back end (multiple of 32)
 	int state_words;
 	const uint32_t *carry_in; // [n_ch][state_words]
 	uint32_t *carry_out;      // [n_ch][state_words]
@@ -563,171 +564,203 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 	}
 }
 
+// geometry of one work item (one CTA stretch of one channel)
+struct Item {
+	int ch, b;
+	long long m_lo;
+	int m_own, m_hi;           // relative to m_lo
+	int box_n0, phase0;
+};
+__device__ __forceinline__ Item make_item(const FmDev &c, const FmCall &k, int work)
+{
+	Item it;
+	it.ch = work / k.n_cta;
+	it.b = work % k.n_cta;
+	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
+	it.box_n0 = (int)carry[ST_BOX_N];
+	it.phase0 = (int)carry[ST_LPR_PHASE];
+	const long long own_lo = (long long)it.b * k.n_own * k.Sf;
+	long long own_hi = own_lo + (long long)k.n_own * k.Sf;
+	if (own_hi > k.n) { own_hi = k.n; }
+	long long buf_lo = own_lo - (long long)k.n_extra * k.Sf;
+	if (buf_lo < 0) { buf_lo = 0; }
+	it.m_lo = dec_before(c, buf_lo, it.box_n0);
+	it.m_own = (int)(dec_before(c, own_lo, it.box_n0) - it.m_lo);
+	it.m_hi = (int)(dec_before(c, own_hi, it.box_n0) - it.m_lo);
+	return it;
+}
+
+// ---- front end of one work item: one segment per thread (tid 0..FM_THREADS-1)
+template <int P, int SPEC>
+__device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, const Item &it, int tid, int16_t *pcm_s)
+{
+	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
+	const long long g = (long long)it.b * k.n_own + (tid - k.n_extra);
+	const long long start = g * k.Sf;
+	if (g < 0 || start >= k.n) { return; }
+	const long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
+	long long t0 = start - k.halo;
+	FrontState<P> s;
+	if (t0 <= 0) { t0 = 0; front_load<P>(s, carry); }
+	else {
+		front_zero<P>(s);
+		if (P == 0) { s.box_n = (int)((t0 + it.box_n0) % c.D); }
+	}
+	unsigned u = (unsigned)(t0 % k.chunk);
+	const long long m0 = dec_before(c, t0, it.box_n0);
+	EmitCtx e;
+	e.pcm = pcm_s; e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
+	e.rel = (int)(m0 - it.m_lo);
+	e.first_in_chunk = 0;
+	if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, it.box_n0) == m0) ? 1 : 0; }
+	// offsets relative to t0 fit 32 bits (a segment plus its halo)
+	const int16_t *__restrict__ in = k.in + 2 * ((size_t)it.ch * (size_t)k.n + (size_t)t0);
+	const int t_last = (int)(end - t0) - 8;
+	front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u);
+	front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u);
+	if (end == k.n) {
+		// this thread saw the end of the stream: its registers are the next call's carry
+		front_store<P>(s, k.carry_out + (size_t)it.ch * k.state_words);
+	}
+}
+
+// ---- back end of one work item: `lanes` threads (whole warps), one contiguous run of OUTPUTS each.
+// Pieces start on resampler group boundaries, so the only state a piece inherits is the de-emphasis
+// average.
+struct Piece { long long oa, ob; int ga, acc0, ph0; };
+
+__device__ __forceinline__ Piece make_piece(const FmDev &c, const Item &it, const uint32_t *carry, long long o_first,
+                                            long long o_end, int per, int q)
+{
+	Piece p;
+	p.oa = o_first + (long long)q * per;
+	p.ob = p.oa + per;
+	if (p.oa > o_end) { p.oa = o_end; }
+	if (p.ob > o_end) { p.ob = o_end; }
+	p.ga = (int)(group_start(c, p.oa, it.phase0) - it.m_lo);        // buffer-relative PCM index
+	const bool at_origin = (it.m_lo == 0 && p.ga == 0);               // stream start: the carry is the state
+	p.acc0 = at_origin ? (int)carry[ST_LPR_ACC] : 0;
+	p.ph0 = c.resample ? (int)(((long long)it.phase0 + (it.m_lo + p.ga) * (long long)c.slow - p.oa * (long long)c.fast)) : 0;
+	return p;
+}
+
+__device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, const Piece &p,
+                                          int &m_run, int &avg)
+{
+	m_run = p.ga;
+	if (c.a_even) { back_outputs<true>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0); }
+	else { back_outputs<false>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0); }
+}
+
+#define FM_BE_MAX_LANES 256
+#define BAR_BE 1                 // named barrier of the back-end warps (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
+                                          const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok)
+{
+	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
+	int16_t *__restrict__ out = k.out + (size_t)it.ch * (size_t)k.out_stride;
+	const bool last_cta = (it.b == k.n_cta - 1);
+	const long long o_first = out_before(c, it.m_lo + it.m_own, it.phase0);
+	const long long o_end = out_before(c, it.m_lo + it.m_hi, it.phase0);
+	const int n_out = (int)(o_end - o_first);
+	int per = (n_out + lanes - 1) / lanes;
+	if (per < 1) { per = 1; }
+	const int last_q = n_out > 0 ? (n_out - 1) / per : 0;
+	{
+		const Piece p = make_piece(c, it, carry, o_first, o_end, per, q);
+		const bool active = p.oa < p.ob;
+		int lo = -32768, hi = 32767, avg = 0, m_run = p.ga;
+		bool start_ok = true;
+		if (active || q == 0) {
+			int ws = p.ga - k.W_dec;
+			if (ws < 0) { ws = 0; }
+			if (it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
+			if (c.deemph) {
+				if (c.a_even) { back_replay<true>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, p.ga, lo, hi); }
+			}
+			start_ok = !c.deemph || (lo == hi);
+			avg = lo;
+		}
+		if (active && start_ok) { run_piece(c, pcm_s, out, p, m_run, avg); }
+		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = start_ok ? 1 : 0;
+	}
+	bar_sync(BAR_BE, lanes);
+	if (q != 0) { return; }
+	// Pieces whose bracket was still open take their left neighbour's exact end state, left to right
+	// (piece 0: the previous item of this channel, an older ticket, through its published word).
+	for (int j = 0; j <= last_q; j++) {
+		if (s_ok[j]) { continue; }
+		int avg;
+		if (j == 0) {
+			volatile int *pp = k.pub + 4 * (size_t)(work - 1);
+			while (pp[0] == 0) { __nanosleep(64); }
+			__threadfence();
+			avg = pp[1];
+		} else { avg = s_avg[j - 1]; }
+		const Piece p = make_piece(c, it, carry, o_first, o_end, per, j);
+		int m_run = p.ga;
+		if (p.oa < p.ob) { run_piece(c, pcm_s, out, p, m_run, avg); }
+		s_avg[j] = avg; s_mrun[j] = m_run; s_ok[j] = 1;
+		atomicAdd(k.fix_count, 1);
+	}
+	// end state of the item = state after its last piece
+	int fin_avg = s_avg[last_q];
+	const int fin_m = s_mrun[last_q];
+	if (!last_cta) {
+		volatile int *mp = k.pub + 4 * (size_t)work;
+		mp[1] = fin_avg;
+		__threadfence();
+		mp[0] = 1;
+	} else {
+		// tail of the stream: samples after the last emitted output stay in the accumulator
+		int acc = (it.m_lo == 0 && fin_m == 0) ? (int)carry[ST_LPR_ACC] : 0;
+		for (int m = fin_m; m < it.m_hi; m++) {
+			int x = (int)pcm_s[pcm_phys(m)];
+			if (c.deemph) { fin_avg = deemph_step(c, fin_avg, x); x = wrap16(fin_avg); }
+			acc = add_w(acc, x);
+		}
+		uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
+		co[ST_AVG] = (uint32_t)fin_avg;
+		co[ST_LPR_ACC] = (uint32_t)(c.resample ? acc : 0);
+		co[ST_LPR_PHASE] = c.resample ? (uint32_t)(((long long)it.phase0 + (it.m_lo + it.m_hi) * (long long)c.slow) % (long long)c.fast) : 0u;
+		co[ST_SQ_HITS] = carry[ST_SQ_HITS];
+	}
+}
+
+// Persistent CTA of 256 threads: all warps run the front end of a work item, then the first
+// `be_lanes/32` warps run the back end out of the shared PCM buffer.  Work items are handed out by an
+// atomic ticket, oldest first (the cross-item look-back only ever waits for an older ticket).
 template <int P, int SPEC>
 __global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
+	__shared__ int s_avg[FM_BE_MAX_LANES], s_mrun[FM_BE_MAX_LANES];
+	__shared__ unsigned char s_ok[FM_BE_MAX_LANES];
 	const int tid = threadIdx.x;
 	const int total_work = k.n_ch * k.n_cta;
+	const bool direct = Spec<SPEC>::direct(k);
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) { s_work = atomicAdd(k.ticket, 1); }
 		__syncthreads();
 		const int work = s_work;
 		if (work >= total_work) { break; }
-		const int ch = work / k.n_cta;
-		const int b = work % k.n_cta;
-		const uint32_t *carry = k.carry_in + (size_t)ch * k.state_words;
-		const int box_n0 = (int)carry[ST_BOX_N];
-		const int phase0 = (int)carry[ST_LPR_PHASE];
-		int16_t *__restrict__ out = k.out + (size_t)ch * (size_t)k.out_stride;
-		const long long own_lo = (long long)b * k.n_own * k.Sf;
-		long long own_hi = own_lo + (long long)k.n_own * k.Sf;
-		if (own_hi > k.n) { own_hi = k.n; }
-		long long buf_lo = own_lo - (long long)k.n_extra * k.Sf;
-		if (buf_lo < 0) { buf_lo = 0; }
-		const long long m_lo = dec_before(c, buf_lo, box_n0);
-		const int m_own = (int)(dec_before(c, own_lo, box_n0) - m_lo);     // relative to m_lo from here on
-		const int m_hi = (int)(dec_before(c, own_hi, box_n0) - m_lo);
-
-		// ---------------- front end: one segment per thread
-		{
-			const long long g = (long long)b * k.n_own + (tid - k.n_extra);
-			const long long start = g * k.Sf;
-			if (g >= 0 && start < k.n) {
-				const long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
-				long long t0 = start - k.halo;
-				FrontState<P> s;
-				if (t0 <= 0) { t0 = 0; front_load<P>(s, carry); }
-				else {
-					front_zero<P>(s);
-					if (P == 0) { s.box_n = (int)((t0 + box_n0) % c.D); }
-				}
-				unsigned u = (unsigned)(t0 % k.chunk);
-				const long long m0 = dec_before(c, t0, box_n0);
-				EmitCtx e;
-				e.pcm = pcm_s; e.out = out; e.m_lo = m_lo;
-				e.rel = (int)(m0 - m_lo);
-				e.first_in_chunk = 0;
-				if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, box_n0) == m0) ? 1 : 0; }
-				// offsets relative to t0 fit 32 bits (a segment plus its halo)
-				const int16_t *__restrict__ in = k.in + 2 * ((size_t)ch * (size_t)k.n + (size_t)t0);
-				const int t_last = (int)(end - t0) - 8;
-				front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u);
-				front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u);
-				if (end == k.n) {
-					// this thread saw the end of the stream: its registers are the next call's carry
-					front_store<P>(s, k.carry_out + (size_t)ch * k.state_words);
-				}
-			}
-		}
-		if (Spec<SPEC>::direct(k)) {
-			if (tid == 0 && b == k.n_cta - 1) {
-				uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
+		const Item it = make_item(c, k, work);
+		front_item<P, SPEC>(c, k, it, tid, pcm_s);
+		if (direct) {
+			if (tid == 0 && it.b == k.n_cta - 1) {
+				const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
+				uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
 				co[ST_AVG] = carry[ST_AVG]; co[ST_LPR_ACC] = carry[ST_LPR_ACC]; co[ST_LPR_PHASE] = carry[ST_LPR_PHASE];
 				co[ST_SQ_HITS] = carry[ST_SQ_HITS];
 			}
 			continue;
 		}
 		__syncthreads();
-
-		// ---------------- back end: warp 0, one contiguous run of OUTPUTS per lane.  Pieces start on
-		// resampler group boundaries, so the only state a piece inherits is the de-emphasis average.
-		if (tid < 32) {
-			const int lane = tid;
-			const bool last_cta = (b == k.n_cta - 1);
-			const long long o_first = out_before(c, m_lo + m_own, phase0);
-			const long long o_end = out_before(c, m_lo + m_hi, phase0);
-			const int n_out = (int)(o_end - o_first);
-			int per = (n_out + 31) / 32;
-			if (per < 1) { per = 1; }
-			long long oa = o_first + (long long)lane * per;
-			long long ob = oa + per;
-			if (oa > o_end) { oa = o_end; }
-			if (ob > o_end) { ob = o_end; }
-			const bool active = oa < ob;
-			const int last_lane = n_out > 0 ? (n_out - 1) / per : 0;
-			const int ga = (int)(group_start(c, oa, phase0) - m_lo);        // buffer-relative PCM indices
-			int lo = -32768, hi = 32767;
-			int avg = 0, m_run = ga;
-			bool start_ok = true;
-			const bool at_origin = (m_lo == 0 && ga == 0);                  // stream start: carry is the state
-			if (active || lane == 0) {
-				int ws = ga - k.W_dec;
-				if (ws < 0) { ws = 0; }
-				if (m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
-				if (c.deemph) {
-					if (c.a_even) { back_replay<true>(c, pcm_s, ws, ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, ga, lo, hi); }
-				}
-				start_ok = !c.deemph || (lo == hi);
-				if (b == 0 && lane == 0) { start_ok = true; }
-				avg = lo;
-			}
-			const int acc0 = at_origin ? (int)carry[ST_LPR_ACC] : 0;
-			const int ph0 = c.resample ? (int)(((long long)phase0 + (m_lo + ga) * (long long)c.slow - oa * (long long)c.fast)) : 0;
-			if (active && start_ok) {
-				if (c.a_even) { back_outputs<true>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
-				else { back_outputs<false>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
-			}
-			// lanes whose bracket was still open take their left neighbour's end state, left to right
-			bool need = (active || lane == 0) && !start_ok;
-			bool end_exact = !need;
-			int pred_avg = 0;
-			for (int round = 0; round < 34; round++) {
-				unsigned need_mask = __ballot_sync(0xffffffffu, need);
-				if (need_mask == 0u) { break; }
-				int up_avg = __shfl_up_sync(0xffffffffu, avg, 1);
-				int up_ok = __shfl_up_sync(0xffffffffu, end_exact ? 1 : 0, 1);
-				bool can = false;
-				if (need) {
-					if (lane == 0) {
-						// left neighbour is the previous CTA of this channel (older ticket): wait for its end state
-						volatile int *pp = k.pub + 4 * (size_t)(work - 1);
-						while (pp[0] == 0) { __nanosleep(64); }
-						__threadfence();
-						pred_avg = pp[1];
-						can = true;
-					} else if (up_ok) {
-						pred_avg = up_avg;
-						can = true;
-					}
-				}
-				if (can) {
-					avg = pred_avg; m_run = ga;
-					if (active) {
-						if (c.a_even) { back_outputs<true>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
-						else { back_outputs<false>(c, pcm_s, out, oa, ob, m_run, avg, acc0, ph0); }
-					}
-					need = false; end_exact = true;
-					atomicAdd(k.fix_count, 1);
-				}
-			}
-			// end state of the CTA = state of its last active lane (lane 0 when it produced nothing)
-			int fin_avg = __shfl_sync(0xffffffffu, avg, last_lane);
-			int fin_m = __shfl_sync(0xffffffffu, m_run, last_lane);
-			if (lane == 0) {
-				if (!last_cta) {
-					volatile int *mp = k.pub + 4 * (size_t)work;
-					mp[1] = fin_avg;
-					__threadfence();
-					mp[0] = 1;
-				} else {
-					// tail of the stream: samples after the last emitted output stay in the accumulator
-					int acc = (m_lo == 0 && fin_m == 0) ? (int)carry[ST_LPR_ACC] : 0;
-					for (int m = fin_m; m < m_hi; m++) {
-						int x = (int)pcm_s[pcm_phys(m)];
-						if (c.deemph) { fin_avg = deemph_step(c, fin_avg, x); x = wrap16(fin_avg); }
-						acc = add_w(acc, x);
-					}
-					uint32_t *co = k.carry_out + (size_t)ch * k.state_words;
-					co[ST_AVG] = (uint32_t)fin_avg;
-					co[ST_LPR_ACC] = (uint32_t)(c.resample ? acc : 0);
-					co[ST_LPR_PHASE] = c.resample ? (uint32_t)(((long long)phase0 + (m_lo + m_hi) * (long long)c.slow) % (long long)c.fast) : 0u;
-					co[ST_SQ_HITS] = carry[ST_SQ_HITS];
-				}
-			}
-		}
+		if (tid < k.be_lanes) { back_item(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok); }
 	}
 }
 
@@ -1022,31 +1055,56 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		if (Sf < 4 * halo) { Sf = 4 * halo; }
 	}
 	Sf = round_up_ll(Sf, G);
-	long long n_extra, n_own, stretch, n_cta, ppt, pcm_cap;
-	size_t smem;
-	for (;;) {
-		n_extra = direct_out ? 0 : (margin_dec * Dtot + halo + Sf - 1) / Sf;
-		ppt = Sf / Dtot + 2;
+	const bool sf_forced = (h->tune_seg > 0) || getenv("RXB200_FM_SEG");
+	long long n_extra = 0, n_own = 0, stretch = 0, n_cta = 0, ppt = 0, pcm_cap = 0;
+	size_t smem = 0;
+	auto geometry = [&](long long sf) -> bool {
+		n_extra = direct_out ? 0 : (margin_dec * Dtot + halo + sf - 1) / sf;
+		ppt = sf / Dtot + 2;
 		pcm_cap = direct_out ? 8 : (long long)FM_THREADS * ppt + 64;
 		pcm_cap += 2 * (pcm_cap >> 7) + 8;
 		smem = (size_t)pcm_cap * sizeof(int16_t);
-		if (n_extra > FM_THREADS / 2 && (long long)smem * 2 <= h->smem_optin) {
-			Sf = round_up_ll(Sf * 2, G);          // very long warm-up: lengthen the segments
-			continue;
+		if ((long long)smem > h->smem_optin || n_extra > FM_THREADS / 2) { return false; }
+		n_own = FM_THREADS - n_extra;
+		stretch = n_own * sf;
+		n_cta = (n + stretch - 1) / stretch;
+		return true;
+	};
+	if (!geometry(Sf)) {
+		// long warm-up wants longer segments, a big PCM buffer shorter ones: scan for something that fits
+		bool ok = false;
+		for (long long sf = round_up_ll(Sf * 8, G); sf >= G && !ok; sf = round_up_ll(sf / 2, G)) {
+			if (geometry(sf)) { Sf = sf; ok = true; }
+			if (sf == G) { break; }
 		}
-		if ((long long)smem > h->smem_optin && Sf > G) {
-			Sf = round_up_ll(Sf / 2, G);          // PCM buffer too large: shorten the segments
-			if ((margin_dec * Dtot + halo + Sf - 1) / Sf <= FM_THREADS / 2) { continue; }
+		if (!ok) {
+			set_error("no segment length fits: warm-up %lld samples, D=%lld, shared memory %d", margin_dec * Dtot, Dtot, h->smem_optin);
+			return RXB200_EUNSUPPORTED;
 		}
-		break;
 	}
-	if ((long long)smem > h->smem_optin || n_extra >= FM_THREADS) {
-		set_error("no segment length fits: warm-up %lld samples, D=%lld, shared memory %d", margin_dec * Dtot, Dtot, h->smem_optin);
-		return RXB200_EUNSUPPORTED;
+	RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
+	if (per_sm < 1) { per_sm = 1; }
+	if (!sf_forced) {
+		// tail balancing: work items are handed out to n_sm*per_sm resident CTAs; prefer a slightly shorter
+		// segment when it turns a ragged last wave into full waves (cost = replay overhead x wave round-up)
+		const double slots = (double)h->n_sm * per_sm;
+		long long best = Sf;
+		double best_cost = 1e30;
+		for (long long sf = Sf; sf >= G && sf * 10 >= Sf * 6; sf -= G) {
+			if (!geometry(sf)) { continue; }
+			int occ = per_sm;
+			double waves = (double)(n_cta * h->n_channels) / slots;
+			double cost = (waves <= 1.0 ? 1.0 : ceil(waves) / waves) * (1.0 + (double)halo / (double)sf) *
+			              ((double)FM_THREADS / (double)n_own);
+			(void)occ;
+			if (cost < best_cost - 1e-9) { best_cost = cost; best = sf; }
+		}
+		Sf = best;
+		geometry(Sf);
+		RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
-	n_own = FM_THREADS - n_extra;
-	stretch = n_own * Sf;
-	n_cta = (n + stretch - 1) / stretch;
 	const size_t total_work = (size_t)n_cta * h->n_channels;
 	const size_t need_sync = 4 + 4 * total_work;
 	if (need_sync > h->sync_cap) {
@@ -1060,10 +1118,20 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
 	k.n_ch = h->n_channels; k.Sf = (int)Sf; k.halo = (int)halo; k.n_extra = (int)n_extra; k.n_own = (int)n_own;
 	k.n_cta = (int)n_cta; k.W_dec = (int)W_dec; k.pcm_cap = (int)pcm_cap; k.direct_out = direct_out;
+	{
+		// back-end width: enough lanes that a piece is about half a replay long (more lanes shorten the
+		// phase in which the other warps idle, but every lane pays the full replay)
+		const char *e = getenv("RXB200_FM_BE_LANES");
+		const long long item_pcm = n_own * Sf / Dtot;
+		long long want = W_dec > 0 ? (2 * item_pcm / W_dec + 31) / 32 * 32 : 128;
+		int bl = e ? atoi(e) : (int)want;
+		bl = (bl / 32) * 32;
+		if (bl < 32) { bl = 32; }
+		if (bl > FM_THREADS) { bl = FM_THREADS; }
+		k.be_lanes = bl;
+	}
 	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
 	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
-	RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 1;
 	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	size_t blocks = (size_t)h->n_sm * per_sm;
