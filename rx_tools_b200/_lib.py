@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librxb200.so")
+LIB_PATH = os.environ.get("RXB200_LIB", os.path.join(HERE, "librxb200.so"))   # override: A/B builds of the same ABI
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, EUNSUPPORTED, ECAPACITY = 0, -1, -2, -3, -4, -5, -6
 ERR_NAMES = {EINVAL: "EINVAL", ENODEV: "ENODEV", ECUDA: "ECUDA", ENOMEM: "ENOMEM",

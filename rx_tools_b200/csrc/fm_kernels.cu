@@ -34,6 +34,15 @@
 namespace rxb {
 
 #define FM_THREADS 256
+#ifndef RXB_CHUNK_BRANCH
+#define RXB_CHUNK_BRANCH 1
+#endif
+#ifndef RXB_OCC
+#define RXB_OCC 3
+#endif
+#ifndef RXB_ATAN_V
+#define RXB_ATAN_V 1
+#endif
 #define FM_MAX_PACKED 3          // fifth_order passes run as packed I/Q SWAR (bias keeps lanes unsigned)
 
 // ------------------------------------------------------------------------------ device config
@@ -224,18 +233,42 @@ __device__ __noinline__ int disc_std(int cr, int cj)
 	return (int)(angle / 3.14159 * (double)(1 << 14));
 }
 
-// fast_atan2 (src/rtl_fm.c:485-506), int32 wrap-around preserved.
+// fast_atan2 (src/rtl_fm.c:485-506), int32 wrap-around preserved.  The two branches of the reference
+//   x >= 0: pi/4  - pi/4 * (x - |y|) / (x + |y|)        x < 0: 3pi/4 - pi/4 * (x + |y|) / (|y| - x)
+// share the divisor |x| + |y|; the quotient is bounded by 4096 whenever that divisor is positive (also
+// after wrap-around of the numerator), so one fp32 reciprocal estimate plus an exact integer remainder
+// correction reproduces C's truncating '/'.  A non-positive divisor (only reachable through int32
+// overflow, or x == y == 0) takes the generic path.
 __device__ __forceinline__ int fast_atan2_i(int y, int x)
 {
+#if RXB_ATAN_V == 0
 	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
 	if (x == 0 && y == 0) { return 0; }
-	int ya = y < 0 ? neg_w(y) : y;
-	int ang;
-	// the quotient is bounded by 4096 in magnitude whenever the divisor is positive (also after
-	// int32 wrap-around of the numerator), so the fp32-estimate division is exact; else C semantics
-	if (x >= 0) { ang = sub_w(q1, div_small_quotient(mul_w(q1, sub_w(x, ya)), add_w(x, ya))); }
-	else        { ang = sub_w(q3, div_small_quotient(mul_w(q1, add_w(x, ya)), sub_w(ya, x))); }
+	int ya0 = y < 0 ? neg_w(y) : y;
+	int ang0;
+	if (x >= 0) { ang0 = sub_w(q1, div_small_quotient(mul_w(q1, sub_w(x, ya0)), add_w(x, ya0))); }
+	else        { ang0 = sub_w(q3, div_small_quotient(mul_w(q1, add_w(x, ya0)), sub_w(ya0, x))); }
+	return y < 0 ? neg_w(ang0) : ang0;
+#else
+	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
+	const int ya = y < 0 ? neg_w(y) : y;
+	const bool xneg = x < 0;
+	const int num = mul_w(q1, xneg ? add_w(x, ya) : sub_w(x, ya));
+	const int den = xneg ? sub_w(ya, x) : add_w(x, ya);
+	int q;
+	if (den > 0) {
+		q = __float2int_rz(__int2float_rn(num) * __frcp_rn(__int2float_rn(den)));
+		const int r = sub_w(num, mul_w(q, den));
+		const int up = num >= 0 ? (r >= den ? 1 : 0) : (r > 0 ? 1 : 0);
+		const int dn = num >= 0 ? (r < 0 ? 1 : 0) : (r <= -den ? 1 : 0);
+		q += up - dn;
+	} else {
+		if (x == 0 && y == 0) { return 0; }
+		q = div_c(num, den);
+	}
+	const int ang = sub_w(xneg ? q3 : q1, q);
 	return y < 0 ? neg_w(ang) : ang;
+#endif
 }
 
 // polar_disc_lut (src/rtl_fm.c:528-564)
@@ -551,12 +584,26 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		if (u == 0u) {
 			e.first_in_chunk = 1;
 			// chunk start: every pass forgets the odd sample it was holding
+#if RXB_CHUNK_BRANCH
+			if (true) {
+#pragma unroll
+				for (int l = 0; l < FrontState<P>::PL; l++) {
+#pragma unroll
+					for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
+				}
+			}
+#endif
+		}
+#if !RXB_CHUNK_BRANCH
+		{
+			const bool cs = (u == 0u);
 #pragma unroll
 			for (int l = 0; l < FrontState<P>::PL; l++) {
 #pragma unroll
-				for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
+				for (int j = 5; j > 0; j--) { s.h[l][j] = cs ? s.h[l][j - 1] : s.h[l][j]; }
 			}
 		}
+#endif
 		front_block<P, SPEC, STORE>(c, k, s, e, v, u);
 		u += 8u;
 #pragma unroll
@@ -733,7 +780,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 // `be_lanes/32` warps run the back end out of the shared PCM buffer.  Work items are handed out by an
 // atomic ticket, oldest first (the cross-item look-back only ever waits for an older ticket).
 template <int P, int SPEC>
-__global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? 3 : (P <= 6 ? 2 : 1))) fm_fused_kernel(const FmDev c, const FmCall k)
+__global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
