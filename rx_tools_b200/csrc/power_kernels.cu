@@ -197,6 +197,196 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// power_fft8_kernel<E>: the fast path for the BASELINE shapes (hop buffer = 16384 int16, N = 2^E,
+// 3 <= E <= 13, no decimation).  1024 threads own one hop buffer; every thread keeps EIGHT points
+// of one N-block in registers and runs three fix_fft stages per trip through shared memory.
+//
+// The reference bit-reverses first and then pairs positions p, p + 2^s in stage s
+// (src/rtl_power.c:275-318).  Position p holds input n = rev(p), so the same butterfly graph in
+// NATURAL input order pairs slots n, n + N/2^(s+1) (the slot whose bit is 0 is the reference's
+// "i", the other its "j = i + l"), with twiddle index m = (p mod 2^s) = the top s bits of n,
+// reversed.  Running the graph in natural order needs no permutation pass: after the last stage
+// slot n simply holds bin rev(n), which only matters when the per-thread accumulators are flushed.
+// Every butterfly is the reference's, bit for bit: wr = Sinewave[j + N/4] >> 1, wi = -Sinewave[j] >> 1,
+// FIX_MPY(a,b) = (a*b + 2^14) >> 15, the halving of the "i" input and the int16 wrap of all four
+// results.
+// Shared-memory layout between trips: slot n of a block lives at n + (n / (8*Bw)) * Bw where Bw is
+// the spacing of a thread's eight points in the NEXT trip, so that the 32 lanes of a warp (which
+// differ in the low bits of n and in the bits above the thread's three) hit 32 different banks.
+struct Cx { int re, im; };
+
+__device__ __forceinline__ void bfly(Cx &lo, Cx &hi, int wr, int wi)
+{
+	// lo = reference's x[i], hi = x[j]
+	int tr = q15(wr, hi.re) - q15(wi, hi.im);
+	int ti = q15(wr, hi.im) + q15(wi, hi.re);
+	int qr = lo.re >> 1, qi = lo.im >> 1;
+	hi.re = (int)(int16_t)(qr - tr);
+	hi.im = (int)(int16_t)(qi - ti);
+	lo.re = (int)(int16_t)(qr + tr);
+	lo.im = (int)(int16_t)(qi + ti);
+}
+
+__device__ __forceinline__ void tw_unpack(uint32_t w, int &wr, int &wi) { wr = plo(w); wi = phi(w); }
+
+// three (or, on the last trip, the last `nst`) stages on the eight points x[j], j = (j2 j1 j0)
+template <int E>
+__device__ __forceinline__ void trip_stages(Cx (&x)[8], const uint32_t *tw, int rA, int s0, int first)
+{
+	constexpr int N = 1 << E;
+	int wr, wi;
+	if (first <= 0) {           // stage s0: pairs (j, j+4), one twiddle
+		tw_unpack(tw[rA << (E - 1 - s0)], wr, wi);
+#pragma unroll
+		for (int j = 0; j < 4; j++) { bfly(x[j], x[j + 4], wr, wi); }
+	}
+	if (first <= 1) {           // stage s0+1: pairs (j, j+2), twiddle depends on j2
+#pragma unroll
+		for (int j2 = 0; j2 < 2; j2++) {
+			tw_unpack(tw[(rA << (E - 2 - s0)) + j2 * (N / 4)], wr, wi);
+			bfly(x[4 * j2], x[4 * j2 + 2], wr, wi);
+			bfly(x[4 * j2 + 1], x[4 * j2 + 3], wr, wi);
+		}
+	}
+	{                           // stage s0+2: pairs (j, j+1), twiddle depends on j2, j1
+#pragma unroll
+		for (int jj = 0; jj < 4; jj++) {
+			const int j2 = jj >> 1, j1 = jj & 1;
+			tw_unpack(tw[(rA << (E - 3 - s0)) + j2 * (N / 8) + j1 * (N / 4)], wr, wi);
+			bfly(x[2 * jj], x[2 * jj + 1], wr, wi);
+		}
+	}
+}
+
+template <int E>
+__global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
+{
+	constexpr int N = 1 << E;
+	constexpr int UPB = N / 8;                 // threads per N-block
+	constexpr int NT = (E + 2) / 3;            // trips through shared memory
+	constexpr int REM = E % 3;                 // stages in the last trip when not a multiple of 3
+	constexpr int BUFW = 8192 + 1024;          // words per hop buffer incl. padding
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);                   // two mbarriers
+	long long *red = reinterpret_cast<long long *>(smem_raw + 16);            // 64 x 8 B
+	uint32_t *bufs = reinterpret_cast<uint32_t *>(smem_raw + 16 + 512);       // 2 x BUFW words
+	uint32_t *tw = bufs + 2 * BUFW;                                           // N/2 packed twiddles
+	int16_t *win = reinterpret_cast<int16_t *>(tw + (N / 2 > 4 ? N / 2 : 4)); // N window coefficients
+	const int tid = threadIdx.x;
+	const int hop_local = blockIdx.x / a.slices;
+	const int slice = blockIdx.x % a.slices;
+	const int hop = a.hop_begin + hop_local;
+	const int blk = tid >> (E - 3);
+	const int uu = tid & (UPB - 1);
+
+	// tables: packed twiddles (wr = Sinewave[j + N/4] >> 1, wi = (-Sinewave[j]) >> 1, src/rtl_power.c:298-301)
+	for (int i = tid; i < N / 2; i += 1024) {
+		int wr = (int)a.sine[i + N / 4] >> 1;
+		int wi = (-(int)a.sine[i]) >> 1;
+		tw[i] = ppack(wr, wi);
+	}
+	for (int i = tid; i < N; i += 1024) { win[i] = a.window[i]; }
+	if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+	__syncthreads();
+
+	long long acc[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) { acc[j] = 0; }
+
+	const size_t hop_stride = (size_t)a.n_hops_call * (size_t)a.buf_len;
+	const int16_t *src0 = a.bufs + (size_t)hop_local * (size_t)a.buf_len;
+	if (tid == 0 && slice < a.n_pass) {
+		mbar_expect_tx(&bar[0], 32768u);
+		bulk_load(bufs, src0 + (size_t)slice * hop_stride, 32768u, &bar[0]);
+	}
+	uint32_t parity[2] = {0u, 0u};
+	int it = 0;
+	for (int pass = slice; pass < a.n_pass; pass += a.slices, it++) {
+		const int cur = it & 1;
+		uint32_t *buf = bufs + cur * BUFW;
+		mbar_wait(&bar[cur], parity[cur]);
+		parity[cur] ^= 1u;
+		__syncthreads();                       // everyone is done with the other buffer (previous iteration)
+		if (tid == 0 && pass + a.slices < a.n_pass) {
+			fence_async_smem();
+			mbar_expect_tx(&bar[cur ^ 1], 32768u);
+			bulk_load(bufs + (cur ^ 1) * BUFW, src0 + (size_t)(pass + a.slices) * hop_stride, 32768u, &bar[cur ^ 1]);
+		}
+		// ---- trip 0 loads: n = j*N/8 + uu of block blk, straight from the TMA image
+		uint32_t raw[8];
+		long long si = 0, sq = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			raw[j] = buf[blk * N + j * UPB + uu];
+			si += plo(raw[j]); sq += phi(raw[j]);
+		}
+		// remove_dc over the whole hop buffer (src/rtl_power.c:609-624, :744-745)
+		for (int o = 16; o > 0; o >>= 1) { si += __shfl_down_sync(0xffffffffu, si, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+		if ((tid & 31) == 0) { red[tid >> 5] = si; red[32 + (tid >> 5)] = sq; }
+		__syncthreads();
+		long long ti_ = 0, tq_ = 0;
+#pragma unroll 8
+		for (int w = 0; w < 32; w++) { ti_ += red[w]; tq_ += red[32 + w]; }
+		const int ave_i = (int)(int16_t)(ti_ / 16384LL);
+		const int ave_q = (int)(int16_t)(tq_ / 16383LL);
+		Cx x[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) {      // window multiply with int16 wrap (:749-758)
+			const int w = win[j * UPB + uu];
+			x[j].re = (int)(int16_t)((plo(raw[j]) - ave_i) * w);
+			x[j].im = (int)(int16_t)((phi(raw[j]) - ave_q) * w);
+		}
+#pragma unroll
+		for (int t = 0; t < NT; t++) {
+			const bool last = (t == NT - 1);
+			// geometry of this trip: stages s0, s0+1, s0+2 (the last trip of a non-multiple-of-3 E re-uses
+			// s0 = E-3 and skips the stages an earlier trip already did)
+			const int s0 = (last && REM != 0) ? (E - 3) : 3 * t;
+			const int first = (last && REM != 0) ? (3 - REM) : 0;
+			const int lbw = E - 3 - s0;               // log2 of the spacing of the thread's points
+			const int B = uu & ((1 << lbw) - 1);
+			const int A = uu >> lbw;
+			if (t > 0) {
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					uint32_t w = buf[blk * (N + UPB) + A * (9 << lbw) + (j << lbw) + B];
+					x[j].re = plo(w); x[j].im = phi(w);
+				}
+			}
+			const int rA = s0 > 0 ? (int)(__brev((unsigned)A) >> (32 - (s0 > 0 ? s0 : 1))) : 0;
+			trip_stages<E>(x, tw, rA, s0, first);
+			if (!last) {
+				// store in the layout of the next trip: slot n -> n + (n >> (lbw' + 3)) << lbw'
+				const int s0n = (t + 1 == NT - 1 && REM != 0) ? (E - 3) : 3 * (t + 1);
+				const int lbn = E - 3 - s0n;
+				__syncthreads();               // all loads of this trip are done: the buffer may be rewritten in place
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const int n = (A << (lbw + 3)) + (j << lbw) + B;
+					buf[blk * (N + UPB) + n + ((n >> (lbn + 3)) << lbn)] = ppack(x[j].re, x[j].im);
+				}
+				__syncthreads();
+			}
+		}
+		// real_conj accumulate (:664-668, :760-768): this thread's slots are n = 8*uu + j
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			long long pw = (long long)(x[j].re * x[j].re) + (long long)(x[j].im * x[j].im);
+			if (a.peak_hold) { acc[j] = pw > acc[j] ? pw : acc[j]; } else { acc[j] += pw; }
+		}
+	}
+	// slot n of a block holds bin rev(n)
+	long long *row = a.avg + (size_t)hop * N;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int n = 8 * uu + j;
+		const int bin = (int)(__brev((unsigned)n) >> (32 - E));
+		if (a.peak_hold) { atomicMax(row + bin, acc[j]); }
+		else { atomicAdd(reinterpret_cast<unsigned long long *>(row + bin), (unsigned long long)acc[j]); }
+	}
+}
+
 // rms_power (src/rtl_power.c:403-429): one value per hop buffer.
 __global__ void __launch_bounds__(256) power_rms_kernel(const PowArgs a)
 {
@@ -344,6 +534,32 @@ static cudaError_t launch_fft(const PowArgs &a, int blocks, size_t smem, cudaStr
 	return cudaGetLastError();
 }
 
+template <int E>
+static cudaError_t launch_fft8_e(const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
+{
+	cudaError_t e = cudaFuncSetAttribute(power_fft8_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) { return e; }
+	power_fft8_kernel<E><<<blocks, 1024, smem, st>>>(a);
+	return cudaGetLastError();
+}
+static cudaError_t launch_fft8(int bin_e, const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
+{
+	switch (bin_e) {
+	case 3: return launch_fft8_e<3>(a, blocks, smem, st);
+	case 4: return launch_fft8_e<4>(a, blocks, smem, st);
+	case 5: return launch_fft8_e<5>(a, blocks, smem, st);
+	case 6: return launch_fft8_e<6>(a, blocks, smem, st);
+	case 7: return launch_fft8_e<7>(a, blocks, smem, st);
+	case 8: return launch_fft8_e<8>(a, blocks, smem, st);
+	case 9: return launch_fft8_e<9>(a, blocks, smem, st);
+	case 10: return launch_fft8_e<10>(a, blocks, smem, st);
+	case 11: return launch_fft8_e<11>(a, blocks, smem, st);
+	case 12: return launch_fft8_e<12>(a, blocks, smem, st);
+	case 13: return launch_fft8_e<13>(a, blocks, smem, st);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
 extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_hop_bufs, int n_pass,
                                               int hop_begin, int hop_end, int sync)
 {
@@ -372,6 +588,17 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		const int N = 1 << h->p.bin_e;
 		size_t smem = 16 + 256 + (size_t)h->p.buf_len * 2 + (size_t)((N * 3 / 4 + 7) & ~7) * 2 + (size_t)N * 2;
 		cudaError_t e;
+		const bool fast = (h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !getenv("RXB200_POWER_V1"));
+		if (fast) {
+			// one CTA of 1024 threads per (hop, pass-slice); ~1 CTA per SM resident
+			int sl = (h->n_sm + nh - 1) / nh;
+			if (sl > n_pass) { sl = n_pass; }
+			if (sl < 1) { sl = 1; }
+			a.slices = sl;
+			const size_t sm8 = 16 + 512 + 2 * (8192 + 1024) * 4 + (size_t)(N / 2 > 4 ? N / 2 : 4) * 4 + (size_t)N * 2;
+			e = launch_fft8(h->p.bin_e, a, nh * sl, sm8, h->stream);
+			if (e != cudaSuccess) { set_error("power_fft8_kernel launch: %s", cudaGetErrorString(e)); return RXB200_ECUDA; }
+		} else {
 		const int nb = N / 256;
 		if (nb <= 1) { e = launch_fft<1>(a, blocks, smem, h->stream); }
 		else if (nb == 2) { e = launch_fft<2>(a, blocks, smem, h->stream); }
@@ -380,6 +607,7 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		else if (nb == 16) { e = launch_fft<16>(a, blocks, smem, h->stream); }
 		else { e = launch_fft<0>(a, blocks, smem, h->stream); }
 		if (e != cudaSuccess) { set_error("power_fft_kernel launch: %s", cudaGetErrorString(e)); return RXB200_ECUDA; }
+		}
 		const int per_buf = (h->p.buf_len / h->p.downsample) / (2 * N);
 		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass * per_buf * h->p.downsample; }   // :769
 	}

@@ -88,3 +88,25 @@ def test_literal_vectors():
     avg, smp = sc.read()
     assert np.array_equal(avg, z["pw_avg"]) and np.array_equal(smp, z["pw_samples"])
     sc.close()
+
+
+@pytest.mark.parametrize("bin_e", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("peak", [0, 1])
+def test_every_fft_size(bin_e, peak, port):
+    """All FFT lengths the 16384-int16 hop buffer admits (the register-resident kernel covers 3..13, the generic
+    shared-memory kernel the rest), full-scale input so every int16 wrap in the butterflies is exercised."""
+    n = 1 << bin_e
+    plan = power.Plan(n_hops=3, bin_e=bin_e, buf_len=16384, downsample=1, downsample_passes=0, comp_fir_size=0,
+                      boxcar=1, peak_hold=peak, rate=2000000, crop=0.0, first_freq=100000000, freq_step=2000000,
+                      bin_size_hz=0.0)
+    rng = np.random.default_rng(100 + bin_e)
+    x = rng.integers(-32768, 32768, size=(3, 3, 16384), dtype=np.int32).astype(np.int16)
+    win = power.window_table("blackman", n) if n > 2 else np.array([256, 255][:n], dtype=np.int32)
+    want, ws = port.power_scan(_oracle_params(plan), win, x, 3, 3)
+    sc = power.PowerScanner(plan, win)
+    sc.scanner(x, 3)
+    avg, smp = sc.read()
+    assert np.array_equal(smp, ws)
+    bad = np.argwhere(avg != want)
+    assert bad.size == 0, (bin_e, bad[:4])
+    sc.close()
