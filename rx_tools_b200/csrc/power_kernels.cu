@@ -214,18 +214,25 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 // Shared-memory layout between trips: slot n of a block lives at n + (n / (8*Bw)) * Bw where Bw is
 // the spacing of a thread's eight points in the NEXT trip, so that the 32 lanes of a warp (which
 // differ in the low bits of n and in the bits above the thread's three) hit 32 different banks.
+// A point is kept as a plain int whose LOW 16 bits are its int16 value; the bits above may hold the
+// carry-out of the last add ("unwrapped").  The reference's int16 store is applied where the value
+// is consumed: sign-extended for the multiplies of the "j" input, and folded into the halving of the
+// "i" input ((s << 16) >> 17) — that keeps one shift per value off the ALU pipe, which bounds this
+// kernel.
 struct Cx { int re, im; };
 
 __device__ __forceinline__ void bfly(Cx &lo, Cx &hi, int wr, int wi)
 {
 	// lo = reference's x[i], hi = x[j]
-	int tr = q15(wr, hi.re) - q15(wi, hi.im);
-	int ti = q15(wr, hi.im) + q15(wi, hi.re);
-	int qr = lo.re >> 1, qi = lo.im >> 1;
-	hi.re = (int)(int16_t)(qr - tr);
-	hi.im = (int)(int16_t)(qi - ti);
-	lo.re = (int)(int16_t)(qr + tr);
-	lo.im = (int)(int16_t)(qi + ti);
+	const int vr = (int)(int16_t)hi.re, vi = (int)(int16_t)hi.im;
+	const int tr = q15(wr, vr) - q15(wi, vi);
+	const int ti = q15(wr, vi) + q15(wi, vr);
+	// unsigned shift: the wrap is intended (a signed multiply would let the compiler fold it away)
+	const int qr = (int)((unsigned)lo.re << 16) >> 17, qi = (int)((unsigned)lo.im << 16) >> 17;
+	hi.re = qr - tr;
+	hi.im = qi - ti;
+	lo.re = qr + tr;
+	lo.im = qi + ti;
 }
 
 __device__ __forceinline__ void tw_unpack(uint32_t w, int &wr, int &wi) { wr = plo(w); wi = phi(w); }
@@ -334,8 +341,8 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 #pragma unroll
 		for (int j = 0; j < 8; j++) {      // window multiply with int16 wrap (:749-758)
 			const int w = win[j * UPB + uu];
-			x[j].re = (int)(int16_t)((plo(raw[j]) - ave_i) * w);
-			x[j].im = (int)(int16_t)((phi(raw[j]) - ave_q) * w);
+			x[j].re = (plo(raw[j]) - ave_i) * w;          // low 16 bits = the reference's int16 store
+			x[j].im = (phi(raw[j]) - ave_q) * w;
 		}
 #pragma unroll
 		for (int t = 0; t < NT; t++) {
@@ -372,7 +379,8 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 		// real_conj accumulate (:664-668, :760-768): this thread's slots are n = 8*uu + j
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
-			long long pw = (long long)(x[j].re * x[j].re) + (long long)(x[j].im * x[j].im);
+			const int ur = (int)((unsigned)x[j].re << 16), ui = (int)((unsigned)x[j].im << 16);   // (v << 16)^2 >> 32 == v*v
+			long long pw = (long long)__mulhi(ur, ur) + (long long)__mulhi(ui, ui);
 			if (a.peak_hold) { acc[j] = pw > acc[j] ? pw : acc[j]; } else { acc[j] += pw; }
 		}
 	}
