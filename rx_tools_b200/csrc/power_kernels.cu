@@ -28,6 +28,9 @@ struct PowArgs {
 	const int16_t *window;   // N (low 16 bits of window_coefs; exact, see below)
 	int n_pass, n_hops_call, hop_begin;
 	int buf_len, bin_e, slices, peak_hold;
+	int ds, ds_passes, boxcar, fir_on;   // small-span decimators (src/rtl_power.c:721-743)
+	int fir[6];                          // cic_9_tables[ds_passes][0..5]
+	int tables_in_smem;                  // 0: sine/window stay in global memory (very large N)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +79,99 @@ __device__ __forceinline__ long long block_sum(long long v, long long *red, int 
 	return t;
 }
 
+// ---- small-span decimators, in place on the shared hop buffer (rare path: only when the planner
+// chose downsample > 1).  Every output depends only on ORIGINAL samples at higher (or equal) positions
+// than where it is stored, so each is done in rounds of "all threads read, barrier, all threads write".
+
+// boxcar (src/rtl_power.c:723-733): slot k = int16-wrapped sum of samples [k*ds, (k+1)*ds); the
+// sources are zeroed, so everything past the last slot is zero.
+__device__ void pw_boxcar(uint32_t *buf, int ncomplex, int ds, int tid, int T)
+{
+	const int nslots = (ncomplex + ds - 1) / ds;
+	for (int base = 0; base < nslots; base += T) {
+		const int k = base + tid;
+		int si = 0, sq = 0;
+		if (k < nslots) {
+			int e = (k + 1) * ds < ncomplex ? (k + 1) * ds : ncomplex;
+			for (int i = k * ds; i < e; i++) { uint32_t w = buf[i]; si += plo(w); sq += phi(w); }
+		}
+		__syncthreads();
+		if (k < nslots) { buf[k] = ppack(si, sq); }
+		__syncthreads();
+	}
+	for (int i = nslots + tid; i < ncomplex; i += T) { buf[i] = 0u; }
+	__syncthreads();
+}
+
+// one component (sel 0 = I, 1 = Q) of sample i
+__device__ __forceinline__ int pw_get(const uint32_t *buf, int i, int sel) { return sel ? phi(buf[i]) : plo(buf[i]); }
+__device__ __forceinline__ void pw_put(uint32_t *buf, int i, int sel, int v)
+{
+	uint16_t *h = reinterpret_cast<uint16_t *>(buf + i);
+	h[sel] = (uint16_t)v;
+}
+
+// stateless fifth_order with its "ease-in" head (src/rtl_power.c:582-607) on one component.
+// `length` is the reference's argument (an int16 span); outputs k = 0 .. while 4k < length.
+__device__ void pw_halfband(uint32_t *buf, int length, int sel, int tid, int T)
+{
+	const int nout = (length + 3) / 4 > 3 ? (length + 3) / 4 : 3;
+	for (int base = 0; base < nout; base += T) {
+		const int k = base + tid;
+		int y = 0;
+		if (k < nout) {
+			if (k < 3) {
+				int a = pw_get(buf, 0, sel), b = pw_get(buf, 1, sel), c = pw_get(buf, 2, sel);
+				int d = pw_get(buf, 3, sel), e = pw_get(buf, 4, sel), f = pw_get(buf, 5, sel);
+				if (k == 0) { y = ((a + b) * 10 + (c + d) * 5 + d + f) >> 4; }
+				else if (k == 1) { y = ((b + c) * 10 + (a + d) * 5 + e + f) >> 4; }
+				else { y = (a + (b + e) * 5 + (c + d) * 10 + f) >> 4; }
+			} else {
+				// k = 3: (x2,x3,x4,x5,x5,x6); k = 4: (x4,x5,x5,x6,x7,x8); k >= 5: x[2k-5 .. 2k]
+				int i0, i1, i2, i3, i4, i5;
+				if (k == 3) { i0 = 2; i1 = 3; i2 = 4; i3 = 5; i4 = 5; i5 = 6; }
+				else if (k == 4) { i0 = 4; i1 = 5; i2 = 5; i3 = 6; i4 = 7; i5 = 8; }
+				else { i0 = 2 * k - 5; i1 = i0 + 1; i2 = i0 + 2; i3 = i0 + 3; i4 = i0 + 4; i5 = i0 + 5; }
+				int a = pw_get(buf, i0, sel), b = pw_get(buf, i1, sel), c = pw_get(buf, i2, sel);
+				int d = pw_get(buf, i3, sel), e = pw_get(buf, i4, sel), f = pw_get(buf, i5, sel);
+				y = (a + (b + e) * 5 + (c + d) * 10 + f) >> 4;
+			}
+		}
+		__syncthreads();
+		if (k < nout) { pw_put(buf, k, sel, y); }
+		__syncthreads();
+	}
+}
+
+// stateless generic_fir (src/rtl_power.c:626-654) on one component: samples 0..8 pass through, sample
+// d >= 9 becomes the 9-tap sum over ORIGINAL samples d-9 .. d-1.  Done from the top down so that a
+// round's stores never touch what a later round still has to read.
+__device__ void pw_droop9(uint32_t *buf, int length, int sel, const int *c, int tid, int T)
+{
+	const int ncomp = (length + 1) / 2;           // samples d with 2d < length
+	if (ncomp <= 9) { return; }
+	const int nfil = ncomp - 9;
+	for (int top = nfil; top > 0; top -= T) {
+		const int j = top - 1 - tid;              // filtered index within [0, nfil)
+		int y = 0;
+		if (j >= 0) {
+			const int d = j + 9;
+			int h0 = pw_get(buf, d - 9, sel), h1 = pw_get(buf, d - 8, sel), h2 = pw_get(buf, d - 7, sel);
+			int h3 = pw_get(buf, d - 6, sel), h4 = pw_get(buf, d - 5, sel), h5 = pw_get(buf, d - 4, sel);
+			int h6 = pw_get(buf, d - 3, sel), h7 = pw_get(buf, d - 2, sel), h8 = pw_get(buf, d - 1, sel);
+			int acc = mul_w(h0 + h8, c[1]);
+			acc = add_w(acc, mul_w(h1 + h7, c[2]));
+			acc = add_w(acc, mul_w(h2 + h6, c[3]));
+			acc = add_w(acc, mul_w(h3 + h5, c[4]));
+			acc = add_w(acc, mul_w(h4, c[5]));
+			y = acc >> 15;
+		}
+		__syncthreads();
+		if (j >= 0) { pw_put(buf, j + 9, sel, y); }
+		__syncthreads();
+	}
+}
+
 // NB = bins accumulated in registers per thread (N / blockDim); NB == 0: N too large, accumulate
 // straight into global memory after every block.
 template <int NB>
@@ -87,14 +183,17 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
 	long long *red = reinterpret_cast<long long *>(smem_raw + 16);            // 32 x 8 B
 	uint32_t *buf = reinterpret_cast<uint32_t *>(smem_raw + 16 + 256);        // buf_len/2 words
-	int16_t *sine = reinterpret_cast<int16_t *>(buf + a.buf_len / 2);         // 3N/4
-	int16_t *win = sine + ((N * 3 / 4 + 7) & ~7);                             // N
+	int16_t *sine_s = reinterpret_cast<int16_t *>(buf + a.buf_len / 2);       // 3N/4
+	int16_t *win_s = sine_s + ((N * 3 / 4 + 7) & ~7);                         // N
 	const int hop_local = blockIdx.x / a.slices;
 	const int slice = blockIdx.x % a.slices;
 	const int hop = a.hop_begin + hop_local;
-
-	for (int i = tid; i < N * 3 / 4; i += T) { sine[i] = a.sine[i]; }
-	for (int i = tid; i < N; i += T) { win[i] = a.window[i]; }
+	const int16_t *sine = a.sine, *win = a.window;
+	if (a.tables_in_smem) {
+		for (int i = tid; i < N * 3 / 4; i += T) { sine_s[i] = a.sine[i]; }
+		for (int i = tid; i < N; i += T) { win_s[i] = a.window[i]; }
+		sine = sine_s; win = win_s;
+	}
 	if (tid == 0) { mbar_init(bar, 1); }
 	__syncthreads();
 
@@ -102,8 +201,9 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 #pragma unroll
 	for (int b = 0; b < (NB > 0 ? NB : 1); b++) { acc[b] = 0; }
 
-	const int used = a.buf_len;                 // downsample == 1 on this path
-	const int nblk = used / (2 * N);
+	const int used = a.buf_len / a.ds;          // int16 span after decimation (src/rtl_power.c:744-747)
+	const int nblk = (used + 2 * N - 1) / (2 * N);
+	const int n_i = (used + 1) / 2, n_q = used / 2;   // samples remove_dc touches per component
 	uint32_t parity = 0;
 	for (int pass = slice; pass < a.n_pass; pass += a.slices) {
 		const int16_t *src = a.bufs + ((size_t)pass * a.n_hops_call + hop_local) * (size_t)a.buf_len;
@@ -114,9 +214,23 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 		}
 		mbar_wait(bar, parity);
 		parity ^= 1u;
+		if (a.ds > 1) {
+			__syncthreads();
+			if (a.boxcar) { pw_boxcar(buf, a.buf_len / 2, a.ds, tid, T); }
+			else if (a.ds_passes) {
+				for (int dp = 0; dp < a.ds_passes; dp++) {       // downsample_iq (:656-662)
+					pw_halfband(buf, a.buf_len >> dp, 0, tid, T);
+					pw_halfband(buf, (a.buf_len >> dp) - 1, 1, tid, T);
+				}
+				if (a.fir_on) {
+					pw_droop9(buf, a.buf_len >> a.ds_passes, 0, a.fir, tid, T);
+					pw_droop9(buf, (a.buf_len >> a.ds_passes) - 1, 1, a.fir, tid, T);
+				}
+			}
+		}
 		// remove_dc: sum of one component divided by the int16 span (src/rtl_power.c:609-624)
 		long long si = 0, sq = 0;
-		for (int i = tid; i < used / 2; i += T) { uint32_t w = buf[i]; si += plo(w); sq += phi(w); }
+		for (int i = tid; i < n_i; i += T) { uint32_t w = buf[i]; si += plo(w); if (i < n_q) { sq += phi(w); } }
 		si = block_sum(si, red, tid, T);
 		sq = block_sum(sq, red, tid, T);
 		const int ave_i = (int)(int16_t)(si / (long long)used);
@@ -126,15 +240,17 @@ __global__ void __launch_bounds__(256) power_fft_kernel(const PowArgs a)
 			// window (x - ave) * w with int16 wrap (:749-758) fused with the bit-reversal swap (:275-290)
 			for (int i = tid; i < N; i += T) {
 				int r = (int)(__brev((unsigned)i) >> (32 - a.bin_e));
+				// remove_dc only touched the first n_i / n_q samples of the buffer
+				const int gi = blk * N + i, gr = blk * N + r;
 				if (i < r) {
 					uint32_t u = x[i], v = x[r];
 					int wi_ = win[i], wr_ = win[r];
-					x[r] = ppack((plo(u) - ave_i) * wi_, (phi(u) - ave_q) * wi_);
-					x[i] = ppack((plo(v) - ave_i) * wr_, (phi(v) - ave_q) * wr_);
+					x[r] = ppack((plo(u) - (gi < n_i ? ave_i : 0)) * wi_, (phi(u) - (gi < n_q ? ave_q : 0)) * wi_);
+					x[i] = ppack((plo(v) - (gr < n_i ? ave_i : 0)) * wr_, (phi(v) - (gr < n_q ? ave_q : 0)) * wr_);
 				} else if (i == r) {
 					uint32_t u = x[i];
 					int wi_ = win[i];
-					x[i] = ppack((plo(u) - ave_i) * wi_, (phi(u) - ave_q) * wi_);
+					x[i] = ppack((plo(u) - (gi < n_i ? ave_i : 0)) * wi_, (phi(u) - (gi < n_q ? ave_q : 0)) * wi_);
 				}
 			}
 			__syncthreads();
@@ -441,6 +557,14 @@ __global__ void __launch_bounds__(256) power_rms_kernel(const PowArgs a)
 
 using namespace rxb;
 
+// cic_9_tables (src/rtl_power.c: same table as rtl_fm.c:287-300), first six entries of each row
+static const int k_cic9_power[11][6] = {
+	{0, 0, 0, 0, 0, 0}, {9, -156, -97, 2798, -15489, 61019}, {9, -128, -568, 5593, -24125, 74126},
+	{9, -129, -639, 6187, -26281, 77511}, {9, -122, -612, 6082, -26353, 77818}, {9, -120, -602, 6015, -26269, 77757},
+	{9, -120, -582, 5951, -26128, 77542}, {9, -119, -580, 5931, -26094, 77505}, {9, -119, -578, 5921, -26077, 77484},
+	{9, -119, -577, 5917, -26067, 77473}, {9, -199, -362, 5303, -25505, 77489},
+};
+
 struct rxb200_power {
 	rxb200_power_params p;
 	int device;
@@ -460,12 +584,12 @@ static int power_validate(const rxb200_power_params *p)
 		set_error("bad rx_power parameters"); return RXB200_EINVAL;
 	}
 	if (p->bin_e > 0) {
-		if (p->downsample != 1 || p->downsample_passes != 0) {
-			set_error("rx_power small-span decimators (downsample %d, passes %d) not implemented yet", p->downsample, p->downsample_passes);
-			return RXB200_EUNSUPPORTED;
+		if (p->downsample < 1 || p->downsample_passes < 0 || p->downsample_passes > 10) {
+			set_error("bad downsample %d / passes %d", p->downsample, p->downsample_passes);
+			return RXB200_EINVAL;
 		}
-		long long need = 16 + 256 + (long long)p->buf_len * 2 + (((3LL << p->bin_e) / 4 + 7) & ~7LL) * 2 + (2LL << p->bin_e);
-		if (need > 227 * 1024 || (2 << p->bin_e) > p->buf_len) {
+		long long need = 16 + 256 + (long long)p->buf_len * 2;     // tables move to global memory when they do not fit
+		if (need > 227 * 1024 || (long long)(2 << p->bin_e) * p->downsample > p->buf_len) {
 			set_error("bin_e %d with buf_len %d does not fit shared memory", p->bin_e, p->buf_len);
 			return RXB200_EUNSUPPORTED;
 		}
@@ -581,6 +705,9 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 	a.bufs = d_hop_bufs; a.avg = h->d_avg; a.sine = h->d_sine; a.window = h->d_window;
 	a.n_pass = n_pass; a.n_hops_call = nh; a.hop_begin = hop_begin; a.buf_len = h->p.buf_len;
 	a.bin_e = h->p.bin_e; a.peak_hold = h->p.peak_hold;
+	a.ds = h->p.downsample; a.ds_passes = h->p.downsample_passes; a.boxcar = h->p.boxcar;
+	a.fir_on = (h->p.comp_fir_size == 9 && h->p.downsample_passes >= 1 && h->p.downsample_passes <= 10) ? 1 : 0;
+	for (int j = 0; j < 6; j++) { a.fir[j] = k_cic9_power[h->p.downsample_passes <= 10 ? h->p.downsample_passes : 0][j]; }
 	// enough CTAs for ~4 per SM, never more slices than passes
 	int slices = (h->n_sm * 4 + nh - 1) / nh;
 	if (slices > n_pass) { slices = n_pass; }
@@ -595,8 +722,10 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 	} else {
 		const int N = 1 << h->p.bin_e;
 		size_t smem = 16 + 256 + (size_t)h->p.buf_len * 2 + (size_t)((N * 3 / 4 + 7) & ~7) * 2 + (size_t)N * 2;
+		a.tables_in_smem = 1;
+		if (smem > 227 * 1024) { smem = 16 + 256 + (size_t)h->p.buf_len * 2; a.tables_in_smem = 0; }
 		cudaError_t e;
-		const bool fast = (h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !getenv("RXB200_POWER_V1"));
+		const bool fast = (h->p.downsample == 1 && h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !getenv("RXB200_POWER_V1"));
 		if (fast) {
 			// one CTA of 1024 threads per (hop, pass-slice); ~1 CTA per SM resident
 			int sl = (h->n_sm + nh - 1) / nh;
@@ -616,7 +745,8 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		else { e = launch_fft<0>(a, blocks, smem, h->stream); }
 		if (e != cudaSuccess) { set_error("power_fft_kernel launch: %s", cudaGetErrorString(e)); return RXB200_ECUDA; }
 		}
-		const int per_buf = (h->p.buf_len / h->p.downsample) / (2 * N);
+		const int used_len = h->p.buf_len / h->p.downsample;
+		const int per_buf = (used_len + 2 * N - 1) / (2 * N);
 		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass * per_buf * h->p.downsample; }   // :769
 	}
 	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
