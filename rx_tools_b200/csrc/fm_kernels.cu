@@ -52,6 +52,7 @@ struct FmDev {
 	unsigned a_magic; int a_K, a_use_magic;   // floor(n/a) == umulhi(n, a_magic) for the n range used
 	int resample, fast, slow, lpr_div;
 	int offset_tuning;
+	int squelch, rdc_on, rdc_k, adc_on, adc_k;   // per-chunk reduction stages (src/rtl_fm.c:781-790, :699-721, :684-697)
 	int fir[6];
 	const int *atan_lut;
 };
@@ -77,22 +78,30 @@ struct FmCall {
 	int *ticket;              // work counter
 	int *pub;                 // [n_ch*n_cta][4]  flag, avg, lpr_acc, -
 	int *fix_count;           // lanes that had to be re-run from a neighbour's state
+	// per-chunk scalars of the optional reduction stages, [n_ch][n_chunks]; null when the stage is off
+	const int *rdc;           // [..][2] dc_avgI, dc_avgQ subtracted in that chunk
+	const int *sqz;           // 1: squelch zeroes that chunk
+	const int *adc;           // audio DC average subtracted in that chunk
+	long long *sums;          // [..][2] accumulators of the reduction pre-passes
+	int n_chunks;
+	int reduce_mode;          // 0 main pass, 1 squelch sums (t, p), 2 audio-DC sums
 };
 
 enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC, ST_LPR_PHASE,
        ST_SQ_HITS, ST_ADC, ST_RDC_I, ST_RDC_Q, ST_HDR = 16 };
 
-static inline int fm_packed_levels(int P) { return P < FM_MAX_PACKED ? P : FM_MAX_PACKED; }
-static inline int fm_state_words(int P) { int pl = fm_packed_levels(P); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
+static inline int fm_packed_levels(int P, int wide) { return wide ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED); }
+static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
 
 __device__ __forceinline__ uint32_t pack2(int i, int q) { return ((uint32_t)i & 0xffffu) | ((uint32_t)q << 16); }
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
 // ------------------------------------------------------------------------------ front-end state
-template <int P>
+template <int P, int SPEC>
 struct FrontState {
-	static constexpr int PL = P < FM_MAX_PACKED ? P : FM_MAX_PACKED;
+	// SPEC 2 ("wide"): values may exceed the packed head-room (raw DC block on) -> every pass is scalar
+	static constexpr int PL = (SPEC == 2) ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED);
 	static constexpr int PS = P - PL;
 	int box_i, box_q, box_n;
 	// packed passes: the last six samples the pass has seen (oldest first), I in the low and Q in
@@ -104,17 +113,17 @@ struct FrontState {
 	int pre_i, pre_q;
 };
 
-template <int P>
-__device__ __forceinline__ void front_zero(FrontState<P> &s)
+template <int P, int SPEC>
+__device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 {
 	s.box_i = s.box_q = s.box_n = 0;
 #pragma unroll
-	for (int l = 0; l < FrontState<P>::PL; l++) {
+	for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
 #pragma unroll
 		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l); }
 	}
 #pragma unroll
-	for (int l = 0; l < FrontState<P>::PS; l++) {
+	for (int l = 0; l < FrontState<P, SPEC>::PS; l++) {
 #pragma unroll
 		for (int j = 0; j < 6; j++) { s.wi[l][j] = 0; s.wq[l][j] = 0; }
 		s.pi[l] = 0; s.pq[l] = 0;
@@ -124,10 +133,10 @@ __device__ __forceinline__ void front_zero(FrontState<P> &s)
 	s.pre_i = s.pre_q = 0;
 }
 
-template <int P>
-__device__ __forceinline__ void front_load(FrontState<P> &s, const uint32_t *g)
+template <int P, int SPEC>
+__device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_t *g)
 {
-	constexpr int PL = FrontState<P>::PL, PS = FrontState<P>::PS;
+	constexpr int PL = FrontState<P, SPEC>::PL, PS = FrontState<P, SPEC>::PS;
 	s.box_i = (int)g[ST_BOX_I]; s.box_q = (int)g[ST_BOX_Q]; s.box_n = (int)g[ST_BOX_N];
 	s.pre_i = (int)g[ST_PRE_I]; s.pre_q = (int)g[ST_PRE_Q];
 #pragma unroll
@@ -145,10 +154,10 @@ __device__ __forceinline__ void front_load(FrontState<P> &s, const uint32_t *g)
 	for (int j = 0; j < 9; j++) { s.fh[j] = g[ST_HDR + 6 * PL + 7 * PS + j]; }
 }
 
-template <int P>
-__device__ __forceinline__ void front_store(const FrontState<P> &s, uint32_t *g)
+template <int P, int SPEC>
+__device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32_t *g)
 {
-	constexpr int PL = FrontState<P>::PL, PS = FrontState<P>::PS;
+	constexpr int PL = FrontState<P, SPEC>::PL, PS = FrontState<P, SPEC>::PS;
 	g[ST_BOX_I] = (uint32_t)s.box_i; g[ST_BOX_Q] = (uint32_t)s.box_q; g[ST_BOX_N] = (uint32_t)s.box_n;
 	g[ST_PRE_I] = (uint32_t)s.pre_i; g[ST_PRE_Q] = (uint32_t)s.pre_q;
 #pragma unroll
@@ -181,10 +190,10 @@ __device__ __forceinline__ uint32_t hb_tap(uint32_t a, uint32_t b, uint32_t c, u
 // One input sample at in-chunk index idx of pass L (src/rtl_fm.c:411-440, :765-768): a pass emits at
 // even input indices; index 0 of a chunk slides the window by one (a..e = hist[1..5], f = data[0]),
 // every later even index by two; an odd-indexed sample waits and is lost if the chunk ends on it (F7).
-template <int L, int P>
-__device__ __forceinline__ bool scalar_push(FrontState<P> &s, int xi, int xq, unsigned idx, int &oi, int &oq)
+template <int L, int P, int SPEC>
+__device__ __forceinline__ bool scalar_push(FrontState<P, SPEC> &s, int xi, int xq, unsigned idx, int &oi, int &oq)
 {
-	constexpr int PS = FrontState<P>::PS;
+	constexpr int PS = FrontState<P, SPEC>::PS;
 	if constexpr (L >= PS) {
 		oi = xi; oq = xq;
 		return true;
@@ -201,7 +210,7 @@ __device__ __forceinline__ bool scalar_push(FrontState<P> &s, int xi, int xq, un
 		s.wi[L][5] = xi; s.wq[L][5] = xq;
 		int yi = wrap16((s.wi[L][0] + (s.wi[L][1] + s.wi[L][4]) * 5 + (s.wi[L][2] + s.wi[L][3]) * 10 + s.wi[L][5]) >> 4);
 		int yq = wrap16((s.wq[L][0] + (s.wq[L][1] + s.wq[L][4]) * 5 + (s.wq[L][2] + s.wq[L][3]) * 10 + s.wq[L][5]) >> 4);
-		return scalar_push<L + 1, P>(s, yi, yq, idx >> 1, oi, oq);
+		return scalar_push<L + 1, P, SPEC>(s, yi, yq, idx >> 1, oi, oq);
 	}
 }
 
@@ -311,10 +320,24 @@ __device__ __forceinline__ int deemph_step(const FmDev &c, int avg, int x)
 
 // ------------------------------------------------------------------------------ bookkeeping
 // Decimated samples the reference has produced after t input samples of this call.
-__device__ __forceinline__ long long dec_before(const FmDev &c, long long t, int box_n0)
+__device__ __forceinline__ long long dec_raw(const FmDev &c, long long t, int box_n0)
 {
 	if (c.P > 0) { return t >> c.P; }
 	return (t + box_n0) / c.D;
+}
+// ... and after low_pass_simple's per-chunk grouping (-o, src/rtl_fm.c:373-387): a group counts where
+// its last member is produced (supported shapes make every chunk a whole number of groups).
+__device__ __forceinline__ long long dec_before(const FmDev &c, long long t, int box_n0)
+{
+	long long m = dec_raw(c, t, box_n0);
+	return c.post_ds > 1 ? m / c.post_ds : m;
+}
+// chunk that produced PCM sample m (index after -o grouping, counted from the start of the call)
+__device__ __forceinline__ int pcm_chunk(const FmDev &c, int chunk, long long m, int box_n0)
+{
+	long long md = c.post_ds > 1 ? m * c.post_ds + (c.post_ds - 1) : m;
+	long long pos = c.P > 0 ? (md << c.P) : ((md + 1) * (long long)c.D - box_n0 - 1);
+	return (int)(pos / chunk);
 }
 // Output slot of the first value produced at/after decimated index m.
 __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int phase0)
@@ -344,14 +367,27 @@ struct EmitCtx {
 	long long m_lo;          // decimated index of pcm[0]
 	int rel;                 // decimated index of the next sample, relative to m_lo
 	int first_in_chunk;
+	int chunk_idx;           // chunk the current block belongs to
+	int rdc_i, rdc_q;        // raw DC block offsets of this chunk
+	int sq_zero;             // squelch closed on this chunk
+	int pds_acc, pds_cnt;    // -o group in progress
+	long long red_t, red_p;  // squelch pre-pass accumulators of this chunk
 };
 
 // Everything between the decimator and the serial stages, for one decimated sample.  STORE: the
 // sample belongs to this thread's own segment (otherwise it only advances the filter state).
 template <int P, int SPEC, bool STORE>
-__device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e, int di, int dq)
+__device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int di, int dq)
 {
 	if (c.fir_on) { droop9(s.fh, c.fir, di, dq); }
+	if (SPEC != 1) {
+		if (k.reduce_mode == 1) {       // rms() inputs of this chunk (src/rtl_fm.c:746-751)
+			if (STORE) { e.red_t += di + dq; e.red_p += (long long)di * di + (long long)dq * dq; }
+			e.rel++;
+			return;
+		}
+		if (e.sq_zero) { di = 0; dq = 0; }   // squelch zeroes lowpassed AFTER the droop FIR saw the samples (:785-787)
+	}
 	const int mode = Spec<SPEC>::mode(c);
 	int pcm;
 	if (mode == RXB200_MODE_FM) {
@@ -372,14 +408,19 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 	} else if (mode == RXB200_MODE_LSB) {
 		pcm = mul_w(wrap16(di - dq), c.out_scale);
 	} else {   // raw: lowpassed copied out, nothing after (src/rtl_fm.c:658-665, :809-811)
-		if (STORE) { long long m = e.m_lo + e.rel; e.out[2 * m] = (int16_t)di; e.out[2 * m + 1] = (int16_t)dq; }
+		if (STORE && k.reduce_mode == 0) { long long m = e.m_lo + e.rel; e.out[2 * m] = (int16_t)di; e.out[2 * m + 1] = (int16_t)dq; }
 		e.rel++;
 		e.first_in_chunk = 0;
 		return;
 	}
 	e.first_in_chunk = 0;
+	if (SPEC != 1 && c.post_ds > 1) {   // low_pass_simple: sum of post_ds int16 results, stored as int16 (:373-387)
+		e.pds_acc += wrap16(pcm);
+		if (++e.pds_cnt < c.post_ds) { return; }
+		pcm = e.pds_acc; e.pds_acc = 0; e.pds_cnt = 0;
+	}
 	if (STORE) {      // the int16 store is the reference's (int16_t) cast
-		if (Spec<SPEC>::direct(k)) { e.out[e.m_lo + e.rel] = (int16_t)pcm; }
+		if (Spec<SPEC>::direct(k)) { if (k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
 		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
 	}
 	e.rel++;
@@ -387,9 +428,10 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 
 // scale + fs/4 rotation of one CS16 word (I low, Q high): rotate16_90 multiplies sample n of the chunk by
 // j^n (src/rtl_fm.c:309-327); pos = n & 3 is a compile-time constant in the unrolled block.
-__device__ __forceinline__ void scale_rot(uint32_t w, int pos, bool rotate, int &ri, int &rq)
+__device__ __forceinline__ void scale_rot(uint32_t w, int pos, bool rotate, int &ri, int &rq, int dci = 0, int dcq = 0)
 {
-	int xi = scale_cs16(lo16(w)), xq = scale_cs16(hi16(w));
+	// dc_block_raw_filter subtracts the chunk's running mean between the scale and the rotation (:850-857)
+	int xi = wrap16(scale_cs16(lo16(w)) - dci), xq = wrap16(scale_cs16(hi16(w)) - dcq);
 	if (!rotate) { pos = 0; }
 	switch (pos & 3) {
 	case 1: ri = -xq; rq = xi; break;
@@ -414,23 +456,31 @@ __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
 
 // One block of 8 input samples at in-chunk offset u (multiple of 8).
 template <int P, int SPEC, bool STORE>
-__device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
+__device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
                                             const uint32_t (&v)[8], unsigned u)
 {
-	constexpr int PL = FrontState<P>::PL;
+	constexpr int PL = FrontState<P, SPEC>::PL;
 	const bool rot = Spec<SPEC>::rotate(c);
 	if constexpr (P == 0) {
 		// low_pass boxcar (src/rtl_fm.c:351-371)
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
 			int xi, xq;
-			scale_rot(v[j], j, rot, xi, xq);
+			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
 			s.box_i += xi; s.box_q += xq;
 			if (++s.box_n >= c.D) {
 				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
 				s.box_i = 0; s.box_q = 0; s.box_n = 0;
 				post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
 			}
+		}
+	} else if constexpr (PL == 0) {
+		// "wide" variant: every fifth_order pass scalar with the reference's int16 wrap
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int xi, xq, oi, oq;
+			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
+			if (scalar_push<0, P, SPEC>(s, xi, xq, u + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
 		}
 	} else {
 		uint32_t x[8];
@@ -473,7 +523,7 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 				if constexpr (P > PL) {
 					// in-chunk index of this sample at pass PL: (u >> PL) + j
 					int oi, oq;
-					if (scalar_push<0, P>(s, di, dq, (u >> PL) + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
+					if (scalar_push<0, P, SPEC>(s, di, dq, (u >> PL) + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
 				} else {
 					post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
 				}
@@ -540,9 +590,42 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 // group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
 // group a call inherits from the previous call can start with a larger phase).
 // m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
+// audio DC block bookkeeping of one back-end lane (dc_block_audio_filter, src/rtl_fm.c:684-697)
+struct AdcCtx {
+	const int *adc;          // per-chunk average to subtract (null: stage off or pre-pass)
+	long long *sums;         // pre-pass: per-chunk sum of the de-emphasised samples
+	int chunk, box_n0, n_chunks;
+	long long m_lo;
+	int cur, sub;            // chunk of the running sample, its average
+	long long acc;           // pre-pass accumulator of chunk `cur`
+};
+__device__ __forceinline__ void adc_flush(AdcCtx &a)
+{
+	if (a.sums && a.cur >= 0 && a.acc != 0) { atomicAdd(reinterpret_cast<unsigned long long *>(a.sums + 2 * a.cur), (unsigned long long)a.acc); }
+	a.acc = 0;
+}
+__device__ __forceinline__ int adc_apply(const FmDev &c, AdcCtx &a, int m_rel, int x)
+{
+	const int ch = pcm_chunk(c, a.chunk, a.m_lo + m_rel, a.box_n0);
+	if (ch != a.cur) {
+		adc_flush(a);
+		a.cur = ch;
+		a.sub = a.adc ? a.adc[ch < a.n_chunks ? ch : a.n_chunks - 1] : 0;
+	}
+	if (a.sums) { a.acc += x; }
+	return wrap16(x - a.sub);
+}
+
+// Outputs [oa, ob) of one lane from an exact state: per output, de-emphasise the group's samples,
+// sum them and divide by the integer rate ratio (deemph_filter :673-680, low_pass_real :396-407).
+// `phase` is the resampler phase at the first group's start; right after an emission it is < slow, so a
+// group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
+// group a call inherits from the previous call can start with a larger phase).
+// m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
 template <bool EVEN>
 __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out,
-                                             long long oa, long long ob, int &m, int &avg, int acc, int phase)
+                                             long long oa, long long ob, int &m, int &avg, int acc, int phase,
+                                             AdcCtx *ax, bool store)
 {
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
@@ -560,18 +643,36 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 			int xn = pcm_load(pcm_s, m + 1);      // one entry of slack exists past the last sample
 			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, x + bias, magic, K); x = wrap16(avg); }
 			else if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
+			if (ax) { x = adc_apply(c, *ax, m, x); }
 			acc = add_w(acc, x);
 			x = xn; m++;
 		}
-		out[o] = (int16_t)(c.resample ? div_small_quotient(acc, c.lpr_div) : acc);
+		if (store) { out[o] = (int16_t)(c.resample ? div_small_quotient(acc, c.lpr_div) : acc); }
 		acc = 0;
 	}
 }
 
 // Runs blocks [t, t_end) of one segment; chunk bookkeeping shared by the replay and the owned part.
+// Entering chunk `idx`: flush the reduction pre-pass sums of the chunk just left, fetch the new chunk's scalars.
+template <bool STORE>
+__device__ __forceinline__ void chunk_enter(const FmDev &c, const FmCall &k, EmitCtx &e, int ch, int idx)
+{
+	if (k.reduce_mode == 1 && STORE && (e.red_t != 0 || e.red_p != 0)) {
+		long long *sm = k.sums + 2 * ((size_t)ch * k.n_chunks + e.chunk_idx);
+		atomicAdd(reinterpret_cast<unsigned long long *>(sm), (unsigned long long)e.red_t);
+		atomicAdd(reinterpret_cast<unsigned long long *>(sm + 1), (unsigned long long)e.red_p);
+	}
+	e.red_t = 0; e.red_p = 0;
+	e.chunk_idx = idx;
+	const size_t ci = (size_t)ch * k.n_chunks + (idx < k.n_chunks ? idx : k.n_chunks - 1);
+	if (k.rdc) { e.rdc_i = k.rdc[2 * ci]; e.rdc_q = k.rdc[2 * ci + 1]; }
+	if (k.sqz) { e.sq_zero = k.sqz[ci]; }
+	if (c.post_ds > 1) { e.pds_acc = 0; e.pds_cnt = 0; }       // groups never span chunks
+}
+
 template <int P, int SPEC, bool STORE>
-__device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, FrontState<P> &s, EmitCtx &e,
-                                          const int16_t *__restrict__ in, int t, int t_end, int t_last, unsigned &u)
+__device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
+                                          const int16_t *__restrict__ in, int t, int t_end, int t_last, unsigned &u, int ch)
 {
 	if (t >= t_end) { return; }
 	uint32_t v[8], vn[8];
@@ -583,11 +684,12 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		if (u >= (unsigned)k.chunk) { u = 0u; }
 		if (u == 0u) {
 			e.first_in_chunk = 1;
+			if (SPEC != 1) { chunk_enter<STORE>(c, k, e, ch, e.chunk_idx + 1); }
 			// chunk start: every pass forgets the odd sample it was holding
 #if RXB_CHUNK_BRANCH
 			if (true) {
 #pragma unroll
-				for (int l = 0; l < FrontState<P>::PL; l++) {
+				for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
 #pragma unroll
 					for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
 				}
@@ -598,7 +700,7 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		{
 			const bool cs = (u == 0u);
 #pragma unroll
-			for (int l = 0; l < FrontState<P>::PL; l++) {
+			for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
 #pragma unroll
 				for (int j = 5; j > 0; j--) { s.h[l][j] = cs ? s.h[l][j - 1] : s.h[l][j]; }
 			}
@@ -647,10 +749,10 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	if (g < 0 || start >= k.n) { return; }
 	const long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
 	long long t0 = start - k.halo;
-	FrontState<P> s;
-	if (t0 <= 0) { t0 = 0; front_load<P>(s, carry); }
+	FrontState<P, SPEC> s;
+	if (t0 <= 0) { t0 = 0; front_load<P, SPEC>(s, carry); }
 	else {
-		front_zero<P>(s);
+		front_zero<P, SPEC>(s);
 		if (P == 0) { s.box_n = (int)((t0 + it.box_n0) % c.D); }
 	}
 	unsigned u = (unsigned)(t0 % k.chunk);
@@ -659,15 +761,24 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	e.pcm = pcm_s; e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
 	e.rel = (int)(m0 - it.m_lo);
 	e.first_in_chunk = 0;
-	if (P == 0) { e.first_in_chunk = (dec_before(c, t0 - u, it.box_n0) == m0) ? 1 : 0; }
+	if (P == 0) { e.first_in_chunk = (dec_raw(c, t0 - u, it.box_n0) == dec_raw(c, t0, it.box_n0)) ? 1 : 0; }
+	e.rdc_i = e.rdc_q = 0; e.sq_zero = 0; e.red_t = 0; e.red_p = 0;
+	e.pds_acc = 0; e.pds_cnt = 0; e.chunk_idx = 0;
+	if (SPEC != 1) {
+		e.chunk_idx = (int)(t0 / k.chunk);
+		if (u != 0u) { chunk_enter<false>(c, k, e, it.ch, e.chunk_idx); }   // mid-chunk start: fetch this chunk's scalars
+		else { e.chunk_idx -= 1; }                                           // the first block enters the chunk itself
+		if (c.post_ds > 1) { e.pds_cnt = (int)((dec_raw(c, t0, it.box_n0) - dec_raw(c, t0 - u, it.box_n0)) % c.post_ds); }
+	}
 	// offsets relative to t0 fit 32 bits (a segment plus its halo)
 	const int16_t *__restrict__ in = k.in + 2 * ((size_t)it.ch * (size_t)k.n + (size_t)t0);
 	const int t_last = (int)(end - t0) - 8;
-	front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u);
-	front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u);
-	if (end == k.n) {
+	front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u, it.ch);
+	front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u, it.ch);
+	if (SPEC != 1 && k.reduce_mode == 1) { chunk_enter<true>(c, k, e, it.ch, e.chunk_idx); }   // flush the last chunk's sums
+	if (end == k.n && k.reduce_mode == 0) {
 		// this thread saw the end of the stream: its registers are the next call's carry
-		front_store<P>(s, k.carry_out + (size_t)it.ch * k.state_words);
+		front_store<P, SPEC>(s, k.carry_out + (size_t)it.ch * k.state_words);
 	}
 }
 
@@ -692,17 +803,19 @@ __device__ __forceinline__ Piece make_piece(const FmDev &c, const Item &it, cons
 }
 
 __device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, const Piece &p,
-                                          int &m_run, int &avg)
+                                          int &m_run, int &avg, AdcCtx *ax, bool store)
 {
 	m_run = p.ga;
-	if (c.a_even) { back_outputs<true>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0); }
-	else { back_outputs<false>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0); }
+	if (c.a_even) { back_outputs<true>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
+	else { back_outputs<false>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
+	if (ax) { adc_flush(*ax); }
 }
 
 #define FM_BE_MAX_LANES 256
 #define BAR_BE 1                 // named barrier of the back-end warps (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+template <int SPEC>
 __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
                                           const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok)
 {
@@ -715,6 +828,13 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	int per = (n_out + lanes - 1) / lanes;
 	if (per < 1) { per = 1; }
 	const int last_q = n_out > 0 ? (n_out - 1) / per : 0;
+	const bool store = (SPEC == 1) || (k.reduce_mode == 0);
+	AdcCtx axs;
+	axs.adc = k.adc ? k.adc + (size_t)it.ch * k.n_chunks : nullptr;
+	axs.sums = (k.reduce_mode == 2) ? k.sums + 2 * (size_t)it.ch * k.n_chunks : nullptr;
+	axs.chunk = k.chunk; axs.box_n0 = it.box_n0; axs.n_chunks = k.n_chunks; axs.m_lo = it.m_lo;
+	axs.cur = -1; axs.sub = 0; axs.acc = 0;
+	AdcCtx *ax = (SPEC != 1 && c.adc_on && (axs.adc || axs.sums)) ? &axs : nullptr;
 	{
 		const Piece p = make_piece(c, it, carry, o_first, o_end, per, q);
 		const bool active = p.oa < p.ob;
@@ -730,7 +850,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 			start_ok = !c.deemph || (lo == hi);
 			avg = lo;
 		}
-		if (active && start_ok) { run_piece(c, pcm_s, out, p, m_run, avg); }
+		if (active && start_ok) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
 		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = start_ok ? 1 : 0;
 	}
 	bar_sync(BAR_BE, lanes);
@@ -748,7 +868,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		} else { avg = s_avg[j - 1]; }
 		const Piece p = make_piece(c, it, carry, o_first, o_end, per, j);
 		int m_run = p.ga;
-		if (p.oa < p.ob) { run_piece(c, pcm_s, out, p, m_run, avg); }
+		if (p.oa < p.ob) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
 		s_avg[j] = avg; s_mrun[j] = m_run; s_ok[j] = 1;
 		atomicAdd(k.fix_count, 1);
 	}
@@ -766,13 +886,16 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		for (int m = fin_m; m < it.m_hi; m++) {
 			int x = (int)pcm_s[pcm_phys(m)];
 			if (c.deemph) { fin_avg = deemph_step(c, fin_avg, x); x = wrap16(fin_avg); }
+			if (ax) { x = adc_apply(c, *ax, m, x); }
 			acc = add_w(acc, x);
 		}
-		uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
-		co[ST_AVG] = (uint32_t)fin_avg;
-		co[ST_LPR_ACC] = (uint32_t)(c.resample ? acc : 0);
-		co[ST_LPR_PHASE] = c.resample ? (uint32_t)(((long long)it.phase0 + (it.m_lo + it.m_hi) * (long long)c.slow) % (long long)c.fast) : 0u;
-		co[ST_SQ_HITS] = carry[ST_SQ_HITS];
+		if (ax) { adc_flush(*ax); }
+		if (store) {
+			uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
+			co[ST_AVG] = (uint32_t)fin_avg;
+			co[ST_LPR_ACC] = (uint32_t)(c.resample ? acc : 0);
+			co[ST_LPR_PHASE] = c.resample ? (uint32_t)(((long long)it.phase0 + (it.m_lo + it.m_hi) * (long long)c.slow) % (long long)c.fast) : 0u;
+		}
 	}
 }
 
@@ -780,7 +903,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 // `be_lanes/32` warps run the back end out of the shared PCM buffer.  Work items are handed out by an
 // atomic ticket, oldest first (the cross-item look-back only ever waits for an older ticket).
 template <int P, int SPEC>
-__global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1))) fm_fused_kernel(const FmDev c, const FmCall k)
+__global__ void __launch_bounds__(FM_THREADS, (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1)))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
@@ -797,18 +920,96 @@ __global__ void __launch_bounds__(FM_THREADS, (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 
 		if (work >= total_work) { break; }
 		const Item it = make_item(c, k, work);
 		front_item<P, SPEC>(c, k, it, tid, pcm_s);
-		if (direct) {
-			if (tid == 0 && it.b == k.n_cta - 1) {
+		if (direct || k.reduce_mode == 1) {
+			if (tid == 0 && it.b == k.n_cta - 1 && k.reduce_mode == 0) {
 				const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
 				uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
 				co[ST_AVG] = carry[ST_AVG]; co[ST_LPR_ACC] = carry[ST_LPR_ACC]; co[ST_LPR_PHASE] = carry[ST_LPR_PHASE];
-				co[ST_SQ_HITS] = carry[ST_SQ_HITS];
 			}
 			continue;
 		}
 		__syncthreads();
-		if (tid < k.be_lanes) { back_item(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok); }
+		if (tid < k.be_lanes) { back_item<SPEC>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok); }
 	}
+}
+
+// ---- per-chunk reduction pre-passes: the scalar recurrences across chunks (one thread per channel)
+
+// dc_block_raw_filter (src/rtl_fm.c:699-721): sums of the SCALED I and Q of every chunk
+__global__ void __launch_bounds__(256) fm_rdc_sum_kernel(const int16_t *in, long long n, int chunk, int n_chunks, long long *sums)
+{
+	// grid: (slices, n_chunks, n_ch)
+	const int ch = blockIdx.z, ci = blockIdx.y;
+	const long long c0 = (long long)ci * chunk;
+	long long c1 = c0 + chunk; if (c1 > n) { c1 = n; }
+	const uint32_t *p = reinterpret_cast<const uint32_t *>(in) + (size_t)ch * (size_t)n;
+	long long si = 0, sq = 0;
+	for (long long t = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < c1; t += (long long)gridDim.x * blockDim.x) {
+		uint32_t w = __ldg(p + t);
+		si += scale_cs16(lo16(w)); sq += scale_cs16(hi16(w));
+	}
+	for (int o = 16; o > 0; o >>= 1) { si += __shfl_down_sync(0xffffffffu, si, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+	if ((threadIdx.x & 31) == 0) {
+		long long *sm = sums + 2 * ((size_t)ch * n_chunks + ci);
+		atomicAdd(reinterpret_cast<unsigned long long *>(sm), (unsigned long long)si);
+		atomicAdd(reinterpret_cast<unsigned long long *>(sm + 1), (unsigned long long)sq);
+	}
+}
+
+__global__ void fm_rdc_recur_kernel(const long long *sums, const int *chunk_len, int n_chunks, int n_ch, int kconst,
+                                    const uint32_t *carry_in, uint32_t *carry_out, int state_words, int *rdc)
+{
+	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= n_ch) { return; }
+	int ai = (int)carry_in[(size_t)ch * state_words + ST_RDC_I], aq = (int)carry_in[(size_t)ch * state_words + ST_RDC_Q];
+	for (int ci = 0; ci < n_chunks; ci++) {
+		const long long *sm = sums + 2 * ((size_t)ch * n_chunks + ci);
+		int mi = (int)(sm[0] / (long long)chunk_len[ci]);     // avgI = sumI / (len/2)
+		int mq = (int)(sm[1] / (long long)chunk_len[ci]);
+		ai = div_c(add_w(mi, mul_w(ai, kconst)), kconst + 1);
+		aq = div_c(add_w(mq, mul_w(aq, kconst)), kconst + 1);
+		rdc[2 * ((size_t)ch * n_chunks + ci)] = ai;
+		rdc[2 * ((size_t)ch * n_chunks + ci) + 1] = aq;
+	}
+	carry_out[(size_t)ch * state_words + ST_RDC_I] = (uint32_t)ai;
+	carry_out[(size_t)ch * state_words + ST_RDC_Q] = (uint32_t)aq;
+}
+
+// rms() + squelch decision (src/rtl_fm.c:739-757, :781-790); dec_len = decimated complex samples of the chunk
+__global__ void fm_squelch_kernel(const long long *sums, const int *dec_len, int n_chunks, int n_ch, int level,
+                                  const uint32_t *carry_in, uint32_t *carry_out, int state_words, int *sqz)
+{
+	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= n_ch) { return; }
+	int hits = (int)carry_in[(size_t)ch * state_words + ST_SQ_HITS];
+	for (int ci = 0; ci < n_chunks; ci++) {
+		const long long *sm = sums + 2 * ((size_t)ch * n_chunks + ci);
+		const long long t = sm[0], p = sm[1];
+		const int len = 2 * dec_len[ci];                         // lp_len counts int16
+		// dc = (double)(t*step)/len; err = t*2*dc - dc*dc*len; (int)sqrt((p-err)/len) -- same order, no FMA
+		const double dc = __ddiv_rn((double)t, (double)len);
+		const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), (double)len));
+		const int sr = (int)sqrt(__ddiv_rn(__dsub_rn((double)p, err), (double)len));
+		const int z = sr < level ? 1 : 0;
+		hits = z ? hits + 1 : 0;
+		sqz[(size_t)ch * n_chunks + ci] = z;
+	}
+	carry_out[(size_t)ch * state_words + ST_SQ_HITS] = (uint32_t)hits;
+}
+
+// dc_block_audio_filter recurrence (src/rtl_fm.c:691-696); pcm_len = result_len of the chunk before low_pass_real
+__global__ void fm_adc_recur_kernel(const long long *sums, const int *pcm_len, int n_chunks, int n_ch, int kconst,
+                                    const uint32_t *carry_in, uint32_t *carry_out, int state_words, int *adc)
+{
+	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= n_ch) { return; }
+	int avg = (int)carry_in[(size_t)ch * state_words + ST_ADC];
+	for (int ci = 0; ci < n_chunks; ci++) {
+		int m = (int)(sums[2 * ((size_t)ch * n_chunks + ci)] / (long long)pcm_len[ci]);
+		avg = div_c(add_w(m, mul_w(avg, kconst)), kconst + 1);
+		adc[(size_t)ch * n_chunks + ci] = avg;
+	}
+	carry_out[(size_t)ch * state_words + ST_ADC] = (uint32_t)avg;
 }
 
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
@@ -822,6 +1023,22 @@ static fm_kernel_fn pick_kernel(int P, int spec)
 		case 3: return fm_fused_kernel<3, 1>;
 		case 4: return fm_fused_kernel<4, 1>;
 		default: break;
+		}
+	}
+	if (spec == 2) {
+		switch (P) {
+		case 0: return fm_fused_kernel<0, 2>;
+		case 1: return fm_fused_kernel<1, 2>;
+		case 2: return fm_fused_kernel<2, 2>;
+		case 3: return fm_fused_kernel<3, 2>;
+		case 4: return fm_fused_kernel<4, 2>;
+		case 5: return fm_fused_kernel<5, 2>;
+		case 6: return fm_fused_kernel<6, 2>;
+		case 7: return fm_fused_kernel<7, 2>;
+		case 8: return fm_fused_kernel<8, 2>;
+		case 9: return fm_fused_kernel<9, 2>;
+		case 10: return fm_fused_kernel<10, 2>;
+		default: return nullptr;
 		}
 	}
 	switch (P) {
@@ -880,7 +1097,11 @@ struct rxb200_fm {
 	int tune_seg, tune_warm;
 	rxb200_fm_stats stats;
 	fm_kernel_fn kern;
+	int wide;                      // all-scalar fifth_order passes (raw DC block on)
 	int smem_optin;
+	// per-chunk reduction stages
+	long long *d_sums; int *d_rdc, *d_sqz, *d_adc, *d_lens; size_t chunk_cap;
+	std::vector<int> *h_lens;
 	cudaEvent_t ev0, ev1;
 };
 
@@ -895,10 +1116,7 @@ static int fm_validate(const rxb200_fm_params *p)
 		set_error("low_pass_real needs rate_out >= rate_out2 > 0 (the reference divides by rate_out/rate_out2)");
 		return RXB200_EINVAL;
 	}
-	if (p->post_downsample > 1 || p->squelch_level || p->dc_block_audio || p->dc_block_raw) {
-		set_error("post_downsample / squelch / dc blocks: per-chunk reductions not implemented yet");
-		return RXB200_EUNSUPPORTED;
-	}
+	if (p->post_downsample < 1 || p->post_downsample > 16) { set_error("post_downsample %d", p->post_downsample); return RXB200_EINVAL; }
 	return RXB200_OK;
 }
 
@@ -907,10 +1125,13 @@ static void fm_fill_dev(rxb200_fm *h)
 	const rxb200_fm_params &p = h->p;
 	FmDev &d = h->dev;
 	memset(&d, 0, sizeof d);
-	d.mode = p.mode; d.P = p.downsample_passes; d.PL = fm_packed_levels(d.P);
+	d.mode = p.mode; d.P = p.downsample_passes; d.PL = fm_packed_levels(d.P, h->wide);
+	d.squelch = p.squelch_level; d.rdc_on = p.dc_block_raw ? 1 : 0; d.rdc_k = p.rdc_block_const;
+	d.adc_on = (p.dc_block_audio && p.mode != RXB200_MODE_RAW) ? 1 : 0; d.adc_k = p.adc_block_const;
 	d.D = p.downsample_passes ? (1 << p.downsample_passes) : p.downsample;
 	d.fir_on = (p.downsample_passes > 0 && p.comp_fir_size == 9) ? 1 : 0;
-	d.atan_mode = p.custom_atan; d.out_scale = p.output_scale; d.post_ds = p.post_downsample;
+	d.atan_mode = p.custom_atan; d.out_scale = p.output_scale;
+	d.post_ds = (p.mode != RXB200_MODE_RAW && p.post_downsample > 1) ? p.post_downsample : 1;   // raw_demod returns before -o (:809-811)
 	d.deemph = (p.deemph && p.mode != RXB200_MODE_RAW) ? 1 : 0;
 	d.a = p.deemph ? p.deemph_a : 1; d.a_half = d.a / 2; d.a_even = (d.a % 2 == 0) ? 1 : 0;
 	// reciprocal for floor(n/a) over the numerator range used: verified exhaustively, else fall back to '/'
@@ -946,12 +1167,15 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	if (!h) { return RXB200_ENOMEM; }
 	memset(h, 0, sizeof *h);
 	h->p = *params; h->device = device; h->n_channels = n_channels;
-	h->state_words = fm_state_words(params->downsample_passes);
+	h->wide = params->dc_block_raw ? 1 : 0;
+	h->state_words = fm_state_words(params->downsample_passes, h->wide);
+	h->h_lens = new std::vector<int>();
 	{
 		// wbfm shape: FM + fast_atan2 + rotation, with a serial stage (de-emphasis or resampler)
 		const bool serial = (params->deemph != 0) || (params->rate_out2 > 0);
-		const int spec = (params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
-		                  !params->offset_tuning && serial) ? 1 : 0;
+		const bool plain = !params->squelch_level && !params->dc_block_audio && !params->dc_block_raw && params->post_downsample <= 1;
+		const int spec = h->wide ? 2 : ((params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
+		                                 !params->offset_tuning && serial && plain) ? 1 : 0);
 		h->kern = pick_kernel(params->downsample_passes, spec);
 	}
 	cudaDeviceProp prop;
@@ -984,7 +1208,7 @@ extern "C" int rxb200_fm_reset(rxb200_fm *h)
 	// demod_init (src/rtl_fm.c:1084-1115): everything zero, squelch_hits 11.  A zero sample in a
 	// packed fifth_order history is its bias.
 	std::vector<uint32_t> init((size_t)h->n_channels * h->state_words, 0u);
-	const int PL = fm_packed_levels(h->p.downsample_passes);
+	const int PL = fm_packed_levels(h->p.downsample_passes, h->wide);
 	for (int c = 0; c < h->n_channels; c++) {
 		uint32_t *s = &init[(size_t)c * h->state_words];
 		s[ST_SQ_HITS] = 11u;
@@ -1006,6 +1230,8 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 	cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_sync);
 	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
+	cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens);
+	delete h->h_lens;
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -1031,6 +1257,11 @@ static size_t fm_count_outputs(rxb200_fm *h, size_t n_int16, size_t chunk_int16,
 		long long L = (long long)(len16 / 2), dec;
 		if (p.downsample_passes) { dec = L >> p.downsample_passes; }
 		else { dec = (box_n + L) / p.downsample; box_n = (box_n + L) % p.downsample; }
+		if (h->dev.post_ds > 1) {
+			// low_pass_simple needs a whole number of groups per chunk (otherwise the reference reads stale data)
+			if (dec % h->dev.post_ds != 0) { return (size_t)-1; }
+			dec /= h->dev.post_ds;
+		}
 		long long res;
 		if (p.mode == RXB200_MODE_RAW) { res = 2 * dec; }
 		else if (p.rate_out2 > 0) {
@@ -1084,9 +1315,10 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const long long Dtot = dv.D;
 	const long long G = (1LL << P) > 8 ? (1LL << P) : 8;
 	// front-end replay: decimated samples until cascade (6) + droop FIR (9) + discriminator (1) are exact
-	const long long dec_exact = P ? 18 : 3;
+	const long long dec_exact = (P ? 18 : 3) + (dv.post_ds > 1 ? dv.post_ds : 0);
 	const long long halo = round_up_ll(dec_exact * Dtot, G);
-	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample)) ? 1 : 0;
+	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample && !dv.adc_on)) ? 1 : 0;
+	const long long Dpcm = Dtot * dv.post_ds;   // input samples per PCM sample
 	// back-end replay (decimated samples): de-emphasis bracket + one resampler group
 	long long wd = 0;
 	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
@@ -1097,7 +1329,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	long long Sf = h->tune_seg;
 	if (Sf <= 0) { const char *e = getenv("RXB200_FM_SEG"); Sf = e ? atoll(e) : 0; }
 	if (Sf <= 0) {
-		Sf = 128 * Dtot;
+		Sf = 128 * Dpcm;
 		if (Sf > 2048) { Sf = 2048; }
 		if (Sf < 4 * halo) { Sf = 4 * halo; }
 	}
@@ -1106,8 +1338,8 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	long long n_extra = 0, n_own = 0, stretch = 0, n_cta = 0, ppt = 0, pcm_cap = 0;
 	size_t smem = 0;
 	auto geometry = [&](long long sf) -> bool {
-		n_extra = direct_out ? 0 : (margin_dec * Dtot + halo + sf - 1) / sf;
-		ppt = sf / Dtot + 2;
+		n_extra = direct_out ? 0 : (margin_dec * Dpcm + halo + sf - 1) / sf;
+		ppt = sf / Dpcm + 2;
 		pcm_cap = direct_out ? 8 : (long long)FM_THREADS * ppt + 64;
 		pcm_cap += 2 * (pcm_cap >> 7) + 8;
 		smem = (size_t)pcm_cap * sizeof(int16_t);
@@ -1159,7 +1391,6 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		RXB_CUDA(cudaMalloc(&h->d_sync, need_sync * sizeof(int)));
 		h->sync_cap = need_sync;
 	}
-	RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
 	FmCall k;
 	memset(&k, 0, sizeof k);
 	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
@@ -1169,7 +1400,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		// back-end width: enough lanes that a piece is about half a replay long (more lanes shorten the
 		// phase in which the other warps idle, but every lane pays the full replay)
 		const char *e = getenv("RXB200_FM_BE_LANES");
-		const long long item_pcm = n_own * Sf / Dtot;
+		const long long item_pcm = n_own * Sf / Dpcm;
 		long long want = W_dec > 0 ? (2 * item_pcm / W_dec + 31) / 32 * 32 : 128;
 		int bl = e ? atoi(e) : (int)want;
 		bl = (bl / 32) * 32;
@@ -1179,16 +1410,92 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	}
 	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
 	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
+	const int n_chunks = (int)((n + k.chunk - 1) / k.chunk);
+	k.n_chunks = n_chunks;
 	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	size_t blocks = (size_t)h->n_sm * per_sm;
 	if (blocks > total_work) { blocks = total_work; }
-	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
-	h->kern<<<(unsigned)blocks, FM_THREADS, smem, h->stream>>>(dv, k);
-	RXB_CUDA(cudaGetLastError());
-	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
+	int launches = 0;
+	auto run_fused = [&](int reduce_mode) -> int {
+		k.reduce_mode = reduce_mode;
+		RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
+		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev0, h->stream)); }
+		h->kern<<<(unsigned)blocks, FM_THREADS, smem, h->stream>>>(dv, k);
+		RXB_CUDA(cudaGetLastError());
+		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev1, h->stream)); }
+		launches++;
+		return RXB200_OK;
+	};
+	if (dv.rdc_on || dv.squelch || dv.adc_on) {
+		// per-chunk scalars: sizes (closed form), accumulators, then one recurrence per stage in the
+		// reference's order: raw DC block -> squelch (sees the DC-blocked data) -> audio DC block
+		const size_t cells = (size_t)n_chunks * h->n_channels;
+		if (cells > h->chunk_cap) {
+			cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens);
+			h->d_sums = nullptr; h->d_rdc = h->d_sqz = h->d_adc = h->d_lens = nullptr; h->chunk_cap = 0;
+			RXB_CUDA(cudaMalloc(&h->d_sums, cells * 2 * sizeof(long long)));
+			RXB_CUDA(cudaMalloc(&h->d_rdc, cells * 2 * sizeof(int)));
+			RXB_CUDA(cudaMalloc(&h->d_sqz, cells * sizeof(int)));
+			RXB_CUDA(cudaMalloc(&h->d_adc, cells * sizeof(int)));
+			RXB_CUDA(cudaMalloc(&h->d_lens, (size_t)n_chunks * 3 * sizeof(int)));
+			h->chunk_cap = cells;
+		}
+		std::vector<int> &lens = *h->h_lens;       // [0]: complex per chunk, [1]: decimated per chunk, [2]: PCM per chunk
+		RXB_CUDA(cudaStreamSynchronize(h->stream));   // the previous call may still be reading the host vector
+		lens.assign((size_t)n_chunks * 3, 0);
+		long long box_n = h->h_box_n;
+		for (int ci = 0; ci < n_chunks; ci++) {
+			long long L = (long long)k.chunk < n - (long long)ci * k.chunk ? k.chunk : n - (long long)ci * k.chunk;
+			long long dec = P ? (L >> P) : (box_n + L) / p.downsample;
+			if (!P) { box_n = (box_n + L) % p.downsample; }
+			lens[ci] = (int)L; lens[(size_t)n_chunks + ci] = (int)dec;
+			lens[(size_t)2 * n_chunks + ci] = (int)(dec / dv.post_ds);
+			if (dec < 1) { set_error("a chunk produces no decimated sample"); return RXB200_EUNSUPPORTED; }
+		}
+		RXB_CUDA(cudaMemcpyAsync(h->d_lens, lens.data(), lens.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		const unsigned cb = (unsigned)((h->n_channels + 63) / 64);
+		if (dv.rdc_on) {
+			RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, cells * 2 * sizeof(long long), h->stream));
+			dim3 grid(8, (unsigned)n_chunks, (unsigned)h->n_channels);
+			fm_rdc_sum_kernel<<<grid, 256, 0, h->stream>>>(d_in, n, k.chunk, n_chunks, h->d_sums);
+			RXB_CUDA(cudaGetLastError());
+			fm_rdc_recur_kernel<<<cb, 64, 0, h->stream>>>(h->d_sums, h->d_lens, n_chunks, h->n_channels, dv.rdc_k, k.carry_in, k.carry_out,
+			                                               h->state_words, h->d_rdc);
+			RXB_CUDA(cudaGetLastError());
+			launches += 2;
+			k.rdc = h->d_rdc;
+		}
+		if (dv.squelch) {
+			RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, cells * 2 * sizeof(long long), h->stream));
+			k.sums = h->d_sums;
+			int rc2 = run_fused(1);
+			if (rc2 != RXB200_OK) { return rc2; }
+			fm_squelch_kernel<<<cb, 64, 0, h->stream>>>(h->d_sums, h->d_lens + n_chunks, n_chunks, h->n_channels, dv.squelch, k.carry_in,
+			                                             k.carry_out, h->state_words, h->d_sqz);
+			RXB_CUDA(cudaGetLastError());
+			launches++;
+			k.sqz = h->d_sqz;
+		}
+		if (dv.adc_on) {
+			RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, cells * 2 * sizeof(long long), h->stream));
+			k.sums = h->d_sums;
+			int rc2 = run_fused(2);
+			if (rc2 != RXB200_OK) { return rc2; }
+			fm_adc_recur_kernel<<<cb, 64, 0, h->stream>>>(h->d_sums, h->d_lens + 2 * (size_t)n_chunks, n_chunks, h->n_channels, dv.adc_k,
+			                                               k.carry_in, k.carry_out, h->state_words, h->d_adc);
+			RXB_CUDA(cudaGetLastError());
+			launches++;
+			k.adc = h->d_adc;
+		}
+		k.sums = nullptr;
+	}
+	{
+		int rc2 = run_fused(0);
+		if (rc2 != RXB200_OK) { return rc2; }
+	}
 	h->cur ^= 1;
-	h->stats.launches = 1; h->stats.segments = (int)(total_work * FM_THREADS); h->stats.segment_len = (int)Sf;
+	h->stats.launches = launches; h->stats.segments = (int)(total_work * FM_THREADS); h->stats.segment_len = (int)Sf;
 	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1;
 	return RXB200_OK;
 }
@@ -1203,6 +1510,7 @@ extern "C" int rxb200_fm_process_device(rxb200_fm *h, const int16_t *d_cs16, siz
 	RXB_CUDA(cudaSetDevice(h->device));
 	if (n_int16 == 0) { if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
 	size_t total = fm_count_outputs(h, n_int16, chunk_int16, nullptr, false);
+	if (total == (size_t)-1) { set_error("-o %d needs every chunk to decimate to a multiple of it", h->dev.post_ds); return RXB200_EUNSUPPORTED; }
 	if (total > pcm_stride) { set_error("pcm_stride %zu < %zu outputs", pcm_stride, total); return RXB200_ECAPACITY; }
 	rc = fm_launch(h, d_cs16, n_int16, chunk_int16, d_pcm, pcm_stride);
 	if (rc != RXB200_OK) { return rc; }
@@ -1224,6 +1532,7 @@ extern "C" int rxb200_fm_process(rxb200_fm *h, const int16_t *cs16, size_t n_int
 	RXB_CUDA(cudaSetDevice(h->device));
 	if (n_int16 == 0) { if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
 	size_t total = fm_count_outputs(h, n_int16, chunk_int16, chunk_result_len, false);
+	if (total == (size_t)-1) { set_error("-o %d needs every chunk to decimate to a multiple of it", h->dev.post_ds); return RXB200_EUNSUPPORTED; }
 	if (total > pcm_stride) { set_error("pcm_stride %zu < %zu outputs", pcm_stride, total); return RXB200_ECAPACITY; }
 	size_t in_elems = n_int16 * (size_t)h->n_channels;
 	size_t out_elems = (total + 8) * (size_t)h->n_channels;
