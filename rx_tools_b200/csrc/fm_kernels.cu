@@ -100,7 +100,8 @@ __device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16)
 // ------------------------------------------------------------------------------ front-end state
 template <int P, int SPEC>
 struct FrontState {
-	// SPEC 2 ("wide"): values may exceed the packed head-room (raw DC block on) -> every pass is scalar
+	// SPEC 2: the per-chunk reduction stages are on; values may exceed the packed head-room (raw DC
+	// block) -> every pass is scalar
 	static constexpr int PL = (SPEC == 2) ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED);
 	static constexpr int PS = P - PL;
 	int box_i, box_q, box_n;
@@ -380,7 +381,7 @@ template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int di, int dq)
 {
 	if (c.fir_on) { droop9(s.fh, c.fir, di, dq); }
-	if (SPEC != 1) {
+	if (SPEC == 2) {
 		if (k.reduce_mode == 1) {       // rms() inputs of this chunk (src/rtl_fm.c:746-751)
 			if (STORE) { e.red_t += di + dq; e.red_p += (long long)di * di + (long long)dq * dq; }
 			e.rel++;
@@ -408,19 +409,19 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 	} else if (mode == RXB200_MODE_LSB) {
 		pcm = mul_w(wrap16(di - dq), c.out_scale);
 	} else {   // raw: lowpassed copied out, nothing after (src/rtl_fm.c:658-665, :809-811)
-		if (STORE && k.reduce_mode == 0) { long long m = e.m_lo + e.rel; e.out[2 * m] = (int16_t)di; e.out[2 * m + 1] = (int16_t)dq; }
+		if (STORE && (SPEC != 2 || k.reduce_mode == 0)) { long long m = e.m_lo + e.rel; e.out[2 * m] = (int16_t)di; e.out[2 * m + 1] = (int16_t)dq; }
 		e.rel++;
 		e.first_in_chunk = 0;
 		return;
 	}
 	e.first_in_chunk = 0;
-	if (SPEC != 1 && c.post_ds > 1) {   // low_pass_simple: sum of post_ds int16 results, stored as int16 (:373-387)
+	if (SPEC == 2 && c.post_ds > 1) {   // low_pass_simple: sum of post_ds int16 results, stored as int16 (:373-387)
 		e.pds_acc += wrap16(pcm);
 		if (++e.pds_cnt < c.post_ds) { return; }
 		pcm = e.pds_acc; e.pds_acc = 0; e.pds_cnt = 0;
 	}
 	if (STORE) {      // the int16 store is the reference's (int16_t) cast
-		if (Spec<SPEC>::direct(k)) { if (k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
+		if (Spec<SPEC>::direct(k)) { if (SPEC != 2 || k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
 		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
 	}
 	e.rel++;
@@ -684,7 +685,7 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		if (u >= (unsigned)k.chunk) { u = 0u; }
 		if (u == 0u) {
 			e.first_in_chunk = 1;
-			if (SPEC != 1) { chunk_enter<STORE>(c, k, e, ch, e.chunk_idx + 1); }
+			if (SPEC == 2) { chunk_enter<STORE>(c, k, e, ch, e.chunk_idx + 1); }
 			// chunk start: every pass forgets the odd sample it was holding
 #if RXB_CHUNK_BRANCH
 			if (true) {
@@ -764,7 +765,7 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	if (P == 0) { e.first_in_chunk = (dec_raw(c, t0 - u, it.box_n0) == dec_raw(c, t0, it.box_n0)) ? 1 : 0; }
 	e.rdc_i = e.rdc_q = 0; e.sq_zero = 0; e.red_t = 0; e.red_p = 0;
 	e.pds_acc = 0; e.pds_cnt = 0; e.chunk_idx = 0;
-	if (SPEC != 1) {
+	if (SPEC == 2) {
 		e.chunk_idx = (int)(t0 / k.chunk);
 		if (u != 0u) { chunk_enter<false>(c, k, e, it.ch, e.chunk_idx); }   // mid-chunk start: fetch this chunk's scalars
 		else { e.chunk_idx -= 1; }                                           // the first block enters the chunk itself
@@ -775,8 +776,8 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	const int t_last = (int)(end - t0) - 8;
 	front_run<P, SPEC, false>(c, k, s, e, in, 0, (int)(start - t0), t_last, u, it.ch);
 	front_run<P, SPEC, true>(c, k, s, e, in, (int)(start - t0), (int)(end - t0), t_last, u, it.ch);
-	if (SPEC != 1 && k.reduce_mode == 1) { chunk_enter<true>(c, k, e, it.ch, e.chunk_idx); }   // flush the last chunk's sums
-	if (end == k.n && k.reduce_mode == 0) {
+	if (SPEC == 2 && k.reduce_mode == 1) { chunk_enter<true>(c, k, e, it.ch, e.chunk_idx); }   // flush the last chunk's sums
+	if (end == k.n && (SPEC != 2 || k.reduce_mode == 0)) {
 		// this thread saw the end of the stream: its registers are the next call's carry
 		front_store<P, SPEC>(s, k.carry_out + (size_t)it.ch * k.state_words);
 	}
@@ -828,13 +829,13 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	int per = (n_out + lanes - 1) / lanes;
 	if (per < 1) { per = 1; }
 	const int last_q = n_out > 0 ? (n_out - 1) / per : 0;
-	const bool store = (SPEC == 1) || (k.reduce_mode == 0);
+	const bool store = (SPEC != 2) || (k.reduce_mode == 0);
 	AdcCtx axs;
 	axs.adc = k.adc ? k.adc + (size_t)it.ch * k.n_chunks : nullptr;
 	axs.sums = (k.reduce_mode == 2) ? k.sums + 2 * (size_t)it.ch * k.n_chunks : nullptr;
 	axs.chunk = k.chunk; axs.box_n0 = it.box_n0; axs.n_chunks = k.n_chunks; axs.m_lo = it.m_lo;
 	axs.cur = -1; axs.sub = 0; axs.acc = 0;
-	AdcCtx *ax = (SPEC != 1 && c.adc_on && (axs.adc || axs.sums)) ? &axs : nullptr;
+	AdcCtx *ax = (SPEC == 2 && c.adc_on && (axs.adc || axs.sums)) ? &axs : nullptr;
 	{
 		const Piece p = make_piece(c, it, carry, o_first, o_end, per, q);
 		const bool active = p.oa < p.ob;
@@ -920,8 +921,8 @@ __global__ void __launch_bounds__(FM_THREADS, (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P
 		if (work >= total_work) { break; }
 		const Item it = make_item(c, k, work);
 		front_item<P, SPEC>(c, k, it, tid, pcm_s);
-		if (direct || k.reduce_mode == 1) {
-			if (tid == 0 && it.b == k.n_cta - 1 && k.reduce_mode == 0) {
+		if (direct || (SPEC == 2 && k.reduce_mode == 1)) {
+			if (tid == 0 && it.b == k.n_cta - 1 && (SPEC != 2 || k.reduce_mode == 0)) {
 				const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
 				uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
 				co[ST_AVG] = carry[ST_AVG]; co[ST_LPR_ACC] = carry[ST_LPR_ACC]; co[ST_LPR_PHASE] = carry[ST_LPR_PHASE];
@@ -1167,7 +1168,8 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	if (!h) { return RXB200_ENOMEM; }
 	memset(h, 0, sizeof *h);
 	h->p = *params; h->device = device; h->n_channels = n_channels;
-	h->wide = params->dc_block_raw ? 1 : 0;
+	// any per-chunk reduction stage selects the SPEC 2 kernel (all-scalar passes + stage bookkeeping)
+	h->wide = (params->dc_block_raw || params->squelch_level || params->dc_block_audio || params->post_downsample > 1) ? 1 : 0;
 	h->state_words = fm_state_words(params->downsample_passes, h->wide);
 	h->h_lens = new std::vector<int>();
 	{
