@@ -450,7 +450,7 @@ __device__ __forceinline__ uint32_t scale_rot_pack(uint32_t w, int pos, bool rot
 
 __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
 {
-	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	asm volatile("ld.global.nc.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
 	             : "l"(p));
 }
