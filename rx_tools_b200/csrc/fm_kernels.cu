@@ -37,6 +37,15 @@ namespace rxb {
 #ifndef RXB_CHUNK_BRANCH
 #define RXB_CHUNK_BRANCH 1
 #endif
+#ifndef RXB_L2_CLAMP
+#define RXB_L2_CLAMP 0
+#endif
+#ifndef RXB_L2_MASK
+#define RXB_L2_MASK 31
+#endif
+#ifndef RXB_L2_AHEAD
+#define RXB_L2_AHEAD 64
+#endif
 #ifndef RXB_OCC
 #define RXB_OCC 3
 #endif
@@ -682,6 +691,13 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		// fetch the next block (clamped to the segment's last block) while this one is processed
 		const int tn = t + 8 <= t_last ? t + 8 : t_last;
 		ldg256(in + 2 * (size_t)tn, vn);
+#if RXB_L2_AHEAD > 0
+		// pull the stream into L2 well ahead of the register prefetch (each thread walks its own region)
+		if ((t & RXB_L2_MASK) == 0) {
+			const int tp = min(t + RXB_L2_AHEAD, t_last + RXB_L2_CLAMP);               // never (far) past the segment
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2 * (size_t)tp));
+		}
+#endif
 		if (u >= (unsigned)k.chunk) { u = 0u; }
 		if (u == 0u) {
 			e.first_in_chunk = 1;
@@ -709,6 +725,10 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 #endif
 		front_block<P, SPEC, STORE>(c, k, s, e, v, u);
 		u += 8u;
+		// keep the consumer of the prefetched block BEHIND this block's work: without the (empty) asm the
+		// compiler copies vn right after issuing the load and every warp then waits out the full DRAM latency
+		asm volatile("" : "+r"(vn[0]), "+r"(vn[1]), "+r"(vn[2]), "+r"(vn[3]), "+r"(vn[4]), "+r"(vn[5]), "+r"(vn[6]), "+r"(vn[7])
+		             : "r"(e.rel), "r"(s.pre_i));
 #pragma unroll
 		for (int j = 0; j < 8; j++) { v[j] = vn[j]; }
 	}
