@@ -280,7 +280,7 @@ def run_fm(args, rank, local, world):
         "gpu_launches": stats["launches"] * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "fm_main_kernel", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "fm_fused_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_sample": bytes_per_sample},
         "e2e": e2e,
     }
