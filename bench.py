@@ -266,7 +266,8 @@ def run_fm(args, rank, local, world):
     res = {
         "metric": "I/Q Msamples/s through full_demod() & fix_fft() at 1/2/4/8 B200 vs host CPU",
         "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (args.workload == "fm5a" and not args.size_mib) else "weak", "vs_baseline": None,
         "dtype": "int16/int32 (fp64 atan2 on first sample of each chunk)", "data": "synthetic",
         "config": {"workload": {"fm2b": "rx_fm -M wbfm -s 300k -F 9 -r 48k (2.4 Msps capture -> 48 kHz), fused kernel",
                                 "fm2a": "rx_fm -M wbfm -s 2400000 -r 48000 (D=1), fused kernel",
