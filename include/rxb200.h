@@ -238,6 +238,21 @@ int rxb200_power_kernel_ms(rxb200_power *h, float *ms);
 int rxb200_power_format_row(int64_t *avg_row, int bin_e, int64_t freq, int rate, int downsample,
                             double crop, int samples, char *dst, size_t dst_cap);
 
+/* ======================================================================== rx_sdr
+ * The pointwise sample-format conversions of rx_sdr's recorder loop (src/rtl_sdr.c:348-391):
+ *   RXB200_CVT_CS16_CS8  : (uint8_t)(int)(x/32767.0*128.0+0.4)       per int16 (:367-370)
+ *   RXB200_CVT_CS16_CU8  : (uint8_t)(x/32767.0*128.0+127.4)           per int16 (:375-378)
+ *   RXB200_CVT_CS16_CF32 : x * 1.0f / SHRT_MAX                        per int16 (:383-386)
+ *   RXB200_CVT_CS12_CS16 : 3 packed bytes -> (I, Q) int16             per complex element (:354-362)
+ * n_elems counts COMPLEX elements.  Host pointers; bandwidth-bound, one kernel. */
+#define RXB200_CVT_CS16_CS8  0
+#define RXB200_CVT_CS16_CU8  1
+#define RXB200_CVT_CS16_CF32 2
+#define RXB200_CVT_CS12_CS16 3
+int rxb200_sdr_convert(int kind, const void *src, size_t n_elems, void *dst, int device);
+/* Same with device pointers on `stream` (a cudaStream_t, may be NULL). */
+int rxb200_sdr_convert_device(int kind, const void *d_src, size_t n_elems, void *d_dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -704,3 +704,32 @@ double orx_power_time(const orx_power_params *p, const int *window, const int16_
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ rx_sdr conversions
+ * Restatement of the recorder loop's format conversions (src/rtl_sdr.c:348-391).  PARITY UNPINNED by
+ * execution: the conversions live inline in rx_sdr's main() and cannot be called; the CS8 expression is the
+ * same one rx_fm's callback uses (pinned through libref_fm), the others are single C expressions. */
+void orx_sdr_cs16_to_cs8(const int16_t *src, size_t n_int16, uint8_t *dst)
+{
+	size_t i;
+	for (i = 0; i < n_int16; i++) { dst[i] = (uint8_t)(int)((int16_t)src[i] / 32767.0 * 128.0 + 0.4); }       /* :369 */
+}
+void orx_sdr_cs16_to_cu8(const int16_t *src, size_t n_int16, uint8_t *dst)
+{
+	size_t i;
+	for (i = 0; i < n_int16; i++) { dst[i] = (uint8_t)(int)((int16_t)src[i] / 32767.0 * 128.0 + 127.4); }     /* :377 */
+}
+void orx_sdr_cs16_to_cf32(const int16_t *src, size_t n_int16, float *dst)
+{
+	size_t i;
+	for (i = 0; i < n_int16; i++) { dst[i] = src[i] * 1.0f / 32767; }                                         /* :385, SHRT_MAX */
+}
+void orx_sdr_cs12_to_cs16(const uint8_t *src, size_t n_complex, int16_t *dst)
+{
+	size_t i;
+	for (i = 0; i < n_complex; i++) {                                                                            /* :354-362 */
+		uint8_t b0 = src[3 * i], b1 = src[3 * i + 1], b2 = src[3 * i + 2];
+		dst[2 * i + 0] = (int16_t)((b1 << 12) | (b0 << 4));
+		dst[2 * i + 1] = (int16_t)((b2 << 8) | (b1 & 0xf0));
+	}
+}

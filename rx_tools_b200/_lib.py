@@ -62,6 +62,7 @@ SYMBOLS = [
     "rxb200_power_destroy", "rxb200_power_accumulate", "rxb200_power_accumulate_device", "rxb200_power_read",
     "rxb200_power_device_avg", "rxb200_power_reset", "rxb200_power_stream", "rxb200_power_last_launches",
     "rxb200_power_format_row", "rxb200_power_kernel_ms",
+    "rxb200_sdr_convert", "rxb200_sdr_convert_device",
 ]
 
 _lib = None
@@ -111,6 +112,8 @@ def lib() -> C.CDLL:
     L.rxb200_power_last_launches.argtypes = [C.c_void_p]
     L.rxb200_power_format_row.argtypes = [pi64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                           C.c_char_p, sz]
+    L.rxb200_sdr_convert.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_int]
+    L.rxb200_sdr_convert_device.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

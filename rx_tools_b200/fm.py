@@ -134,3 +134,22 @@ class FmDemod:
         s = _lib.FmStatsC()
         _lib.check(_lib.lib().rxb200_fm_last_stats(self._h, C.byref(s)))
         return {f[0]: int(getattr(s, f[0])) for f in s._fields_}
+
+
+# ---- rx_sdr sample-format conversions (src/rtl_sdr.c:348-391) -------------------------------------------
+CVT_CS16_CS8, CVT_CS16_CU8, CVT_CS16_CF32, CVT_CS12_CS16 = range(4)
+
+
+def sdr_convert(kind: int, src: np.ndarray, device: int = 0) -> np.ndarray:
+    """CS16 (int16 interleaved) -> CS8 / CU8 (uint8 bytes) / CF32 (float32), or packed CS12 (uint8, 3 bytes per
+    complex element) -> CS16."""
+    if kind == CVT_CS12_CS16:
+        s = np.ascontiguousarray(src, dtype=np.uint8)
+        n = s.size // 3
+        out = np.empty(2 * n, dtype=np.int16)
+    else:
+        s = np.ascontiguousarray(src, dtype=np.int16)
+        n = s.size // 2
+        out = np.empty(2 * n, dtype=np.float32 if kind == CVT_CS16_CF32 else np.uint8)
+    _lib.check(_lib.lib().rxb200_sdr_convert(kind, s.ctypes.data, n, out.ctypes.data, device))
+    return out
