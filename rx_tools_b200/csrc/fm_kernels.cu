@@ -1337,7 +1337,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const long long Dtot = dv.D;
 	const long long G = (1LL << P) > 8 ? (1LL << P) : 8;
 	// front-end replay: decimated samples until cascade (6) + droop FIR (9) + discriminator (1) are exact
-	const long long dec_exact = (P ? 18 : 3) + (dv.post_ds > 1 ? dv.post_ds : 0);
+	const long long dec_exact = (P ? (dv.fir_on ? 16 : 8) : 3) + (dv.post_ds > 1 ? dv.post_ds : 0);
 	const long long halo = round_up_ll(dec_exact * Dtot, G);
 	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample && !dv.adc_on)) ? 1 : 0;
 	const long long Dpcm = Dtot * dv.post_ds;   // input samples per PCM sample
