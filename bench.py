@@ -375,6 +375,15 @@ def run_power(args, rank, local, world):
                "h2d_bytes_per_step": int(need * 2), "d2h_bytes_per_step": int(avg.nbytes), "steps": k2}
     peak, peak_src = peaks()
     achieved = samples_rank * 4.0 / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
+    if os.path.exists(tp) and world == 1:
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    fft8 = (plan.downsample == 1 and plan.buf_len == 16384 and 3 <= plan.bin_e <= 13
+            and not os.environ.get("RXB200_POWER_V1"))
     res = {
         "metric": "I/Q Msamples/s through full_demod() & fix_fft() at 1/2/4/8 B200 vs host CPU",
         "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -386,7 +395,8 @@ def run_power(args, rank, local, world):
                    "parallelism": f"hops sharded x{world} + one all_gather of int64 rows" if n_hops > 1 else f"passes sharded x{world}"},
         "gpu_launches": args.steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "power_fft_kernel", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "power_fft8_kernel" if fft8 else "power_fft_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_sample": 4.0},
         "e2e": e2e,
     }
