@@ -78,6 +78,7 @@ static struct {
 	rxb200_fm_cli cli; rxb200_fm_derived der;
 	int conseq_squelch, terminate_on_squelch, squelch_zero, wav, edge, ppm, custom_ppm, bandwidth, verbosity;
 	int direct_sampling, rtlagc;
+	int print_levels, level_no, level_max, level_max_max; double level_sum;   /* -L (src/rtl_fm.c:96-100) */
 	volatile int mute;                 /* int16 to zero at the start of the next read */
 	size_t multiple;                   /* chunk granularity librxb200 accepts */
 	rxb200_fm *fm;
@@ -189,6 +190,20 @@ static void *demod_thread(void *arg)
 		int rc = rxb200_fm_process(G.fm, in->data, in->n, in->n, out->data, 2 * CHUNK_COMPLEX, &n_pcm, NULL);
 		q_end_get(&G.q_raw);
 		if (rc != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); g_stop = 1; n_pcm = 0; }
+		if (G.print_levels && rc == RXB200_OK) {                                  /* :792-806, one chunk per call */
+			int sr = 0; size_t nl = 0;
+			if (rxb200_fm_levels(G.fm, &sr, 1, &nl) == RXB200_OK && nl == 1) {
+				--G.level_no;
+				G.level_sum += sr;
+				if (G.level_max < sr) { G.level_max = sr; }
+				if (G.level_max_max < sr) { G.level_max_max = sr; }
+				if (!G.level_no) {
+					G.level_no = G.print_levels;
+					fprintf(stderr, "%f, %d, %d, %d\n", G.level_sum / G.print_levels, G.level_max, G.level_max_max, squelch);
+					G.level_max = 0; G.level_sum = 0;
+				}
+			}
+		}
 		int hits = 0;
 		if (squelch) { rxb200_fm_squelch_hits(G.fm, &hits); }
 		const int squelch_active = squelch && hits > G.conseq_squelch;            /* :928 */
@@ -239,7 +254,7 @@ int main(int argc, char **argv)
 			break;
 		case 'g': G.gain_str = optarg; break;
 		case 'l': G.cli.squelch_level = (int)atof(optarg); break;
-		case 'L': break;                              /* level printing: host-side diagnostics, not implemented */
+		case 'L': G.print_levels = (int)atof(optarg); break;     /* src/rtl_fm.c:1253 */
 		case 's': G.cli.rate_s = (int)(uint32_t)parse_scaled(optarg); break;
 		case 'r': G.cli.rate_r = (int)parse_scaled(optarg); break;
 		case 'o': fprintf(stderr, "Warning: -o is very buggy\n"); G.cli.post_downsample = (int)atof(optarg); break;
@@ -305,6 +320,8 @@ int main(int argc, char **argv)
 		size_t m = (size_t)2 << G.der.params.downsample_passes;
 		G.multiple = m > 16 ? m : 16;
 	}
+	G.der.params.report_levels = G.print_levels ? 1 : 0;
+	G.level_no = 1;
 	if (rxb200_fm_create(&G.der.params, 0, 1, &G.fm) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); return 1; }
 
 	if (sdr_open(G.dev_query, G.channel, &G.dev, &G.stream) != 0) {

@@ -1,10 +1,10 @@
 /* soapy_fake.c — a replay-only fake of the 32 SoapySDR C entry points rx_tools calls.
  *
- * TEST INFRASTRUCTURE (not product code).  SoapySDR is not installed in this image and the
+ * A REPLAY DEVICE, no DSP: it only hands stored samples to readStream.  SoapySDR is not installed in this image and the
  * reference (rxseger/rx_tools) has no fake device of its own, so this
  * file supplies one.  Two uses:
  *   1. oracle/_ref/libref_fm.so / libref_power.so: the unmodified reference sources are
- *      compiled against oracle/soapy_stub and linked with this file so every symbol
+ *      compiled against host/soapy_replay and linked with this file so every symbol
  *      resolves; the harness feeds samples from memory (soapy_fake_set_memory).
  *   2. the drop-in host shells (host/rx_fm_b200, host/rx_power_b200) run hardware-free
  *      with `-d driver=file,path=capture.cs16[,loop=1]`.

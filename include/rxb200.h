@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RXB200_ABI_VERSION 1
+#define RXB200_ABI_VERSION 2
 
 /* error codes */
 #define RXB200_OK            0
@@ -78,6 +78,7 @@ typedef struct rxb200_fm_params {
 	int dc_block_raw;       /* -E rdc                                                     */
 	int rdc_block_const;    /* -q, default 9                                              */
 	int offset_tuning;      /* 1: skip rotate16_90 (dongle.offset_tuning)                 */
+	int report_levels;      /* -L: keep every chunk's rms() for rxb200_fm_levels          */
 } rxb200_fm_params;
 
 /* CLI-level inputs of rx_fm and what main() + optimal_settings() derive from them
@@ -142,6 +143,12 @@ int rxb200_fm_process_device(rxb200_fm *h, const int16_t *d_cs16, size_t n_int16
 /* squelch_hits after the last processed chunk, per channel (demod.squelch_hits,
  * src/rtl_fm.c:781-790) so the host thread can keep the hop logic of :928-933. */
 int rxb200_fm_squelch_hits(rxb200_fm *h, int *hits /* n_channels */);
+
+/* With params.report_levels: the rms() of every chunk of the LAST process call, laid out
+ * [n_channels][n_chunks] -- the value `sr` that feeds the -L statistics (src/rtl_fm.c:792-806:
+ * the squelch's rms when squelch is on, else rms(lowpassed) after the decimation filters).
+ * n_chunks receives the chunk count of that call; RXB200_ECAPACITY if cap is too small. */
+int rxb200_fm_levels(rxb200_fm *h, int *levels, size_t cap, size_t *n_chunks);
 
 /* The handle's CUDA stream (cudaStream_t) for callers that time or order work themselves. */
 void *rxb200_fm_stream(rxb200_fm *h);

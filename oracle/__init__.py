@@ -133,6 +133,8 @@ class Port:
         L.orx_fm_run.restype = C.c_long
         L.orx_fm_run.argtypes = [C.c_void_p, C.POINTER(C.c_int16), C.c_size_t, C.c_size_t,
                                  C.POINTER(C.c_int16), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orx_fm_run_levels.restype = C.c_long
+        L.orx_fm_run_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int16), C.c_size_t, C.c_size_t, C.POINTER(C.c_int)]
         L.orx_fm_time.restype = C.c_double
         L.orx_fm_time.argtypes = [C.c_void_p, C.POINTER(C.c_int16), C.c_size_t, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_long)]
@@ -178,6 +180,21 @@ class Port:
             raise RuntimeError(f"orx_fm_run failed: {n}")
         res = out[:n].copy()
         return (res, lens[:n_chunks], hits[:n_chunks]) if return_chunks else res
+
+    def fm_levels(self, params: FmParams, cs16: np.ndarray, chunk_int16: int = 262144) -> np.ndarray:
+        """Per-chunk rms() that feeds the -L statistics (src/rtl_fm.c:792-806)."""
+        x = _i16(cs16)
+        pc = params.to_c()
+        h = self.L.orx_fm_new(C.byref(pc))
+        n_chunks = (x.size + chunk_int16 - 1) // chunk_int16
+        lv = np.zeros(max(n_chunks, 1), dtype=np.int32)
+        try:
+            n = self.L.orx_fm_run_levels(h, _p16(x), x.size, chunk_int16, lv.ctypes.data_as(C.POINTER(C.c_int)))
+        finally:
+            self.L.orx_fm_free(h)
+        if n < 0:
+            raise RuntimeError(f"orx_fm_run_levels failed: {n}")
+        return lv[:n_chunks]
 
     def fm_time(self, params: FmParams, cs16: np.ndarray, chunk_int16: int, repeats: int = 1) -> float:
         x = _i16(cs16)
@@ -270,6 +287,8 @@ class RefFm:
         L.ref_fm_run.restype = C.c_long
         L.ref_fm_run.argtypes = [C.POINTER(C.c_int16), C.c_size_t, C.c_size_t, C.POINTER(C.c_int16),
                                  C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_fm_run_levels.restype = C.c_long
+        L.ref_fm_run_levels.argtypes = [C.POINTER(C.c_int16), C.c_size_t, C.c_size_t, C.POINTER(C.c_int)]
         L.ref_fm_time.restype = C.c_double
         L.ref_fm_time.argtypes = [C.POINTER(C.c_int16), C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_long)]
         L.ref_fm_derive.argtypes = [C.c_int] * 11 + [C.POINTER(FmParamsC), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -293,6 +312,18 @@ class RefFm:
             raise RuntimeError(f"ref_fm_run failed: {n}")
         res = out[:n].copy()
         return (res, lens[:n_chunks], hits[:n_chunks]) if return_chunks else res
+
+    def levels(self, params: FmParams, cs16: np.ndarray, chunk_int16: int = 262144) -> np.ndarray:
+        x = _i16(cs16)
+        pc = params.to_c()
+        if self.L.ref_fm_configure(C.byref(pc)) != 0:
+            raise ValueError("bad params")
+        n_chunks = (x.size + chunk_int16 - 1) // chunk_int16
+        lv = np.zeros(max(n_chunks, 1), dtype=np.int32)
+        n = self.L.ref_fm_run_levels(_p16(x), x.size, chunk_int16, lv.ctypes.data_as(C.POINTER(C.c_int)))
+        if n < 0:
+            raise RuntimeError(f"ref_fm_run_levels failed: {n}")
+        return lv[:n_chunks]
 
     def time(self, params: FmParams, cs16: np.ndarray, chunk_int16: int, repeats: int = 1) -> float:
         x = _i16(cs16)

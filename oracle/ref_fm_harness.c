@@ -193,6 +193,29 @@ long ref_fm_run(const int16_t *in, size_t n_int16, size_t chunk_int16,
 	return (long)w;
 }
 
+/* Per-chunk `sr` of the -L statistics (src/rtl_fm.c:792-806): the level counters are file-scope
+ * statics of the included source; with the print period pushed out of reach, levelSum grows by
+ * exactly sr per full_demod() call.  Output PCM is discarded.  Returns the chunk count. */
+long ref_fm_run_levels(const int16_t *in, size_t n_int16, size_t chunk_int16, int *levels)
+{
+	static int16_t tmp[MAXIMUM_BUF_LENGTH];
+	size_t pos = 0, c = 0;
+	if (chunk_int16 == 0 || chunk_int16 > MAXIMUM_BUF_LENGTH) { return -2; }
+	printLevels = 1 << 30; printLevelNo = 1 << 30; levelSum = 0.0; levelMax = 0; levelMaxMax = 0;
+	while (pos < n_int16) {
+		size_t len = n_int16 - pos;
+		double before = levelSum;
+		if (len > chunk_int16) { len = chunk_int16; }
+		memcpy(tmp, in + pos, len * 2);
+		rtlsdr_callback(tmp, (uint32_t)len, &dongle);
+		full_demod(&demod);
+		levels[c] = (int)(levelSum - before);
+		pos += len; c++;
+	}
+	printLevels = 0; printLevelNo = 1; levelSum = 0.0; levelMax = 0; levelMaxMax = 0;
+	return (long)c;
+}
+
 /* Same loop, timed, output discarded into a scratch ring (for the cpu_baseline / --impl
  * reference legs of bench.py).  Returns seconds. */
 double ref_fm_time(const int16_t *in, size_t n_int16, size_t chunk_int16, int repeats, long *n_out)

@@ -60,6 +60,7 @@ typedef struct {
 	int adc_avg;                         /* dc_avg */
 	int rdc_avg_i, rdc_avg_q;            /* dc_avgI, dc_avgQ */
 	int squelch_hits;
+	int want_levels, last_level;   /* -L: per-chunk rms kept for the caller */
 	int *atan_tab;                       /* atan_lut, :91-93 */
 	int16_t *iq;                         /* lowpassed[] */
 	int16_t *pcm;                        /* result[] */
@@ -397,8 +398,10 @@ static void fm_chunk(orx_fm *o, const int16_t *in, int len)
 	} else {
 		boxcar_decimate(o);
 	}
+	o->last_level = 0;
 	if (o->p.squelch_level) {
 		int level = buffer_rms(o->iq, o->iq_len, 1);
+		o->last_level = level;
 		if (level < o->p.squelch_level) {
 			o->squelch_hits++;
 			memset(o->iq, 0, (size_t)o->iq_len * 2);
@@ -406,6 +409,8 @@ static void fm_chunk(orx_fm *o, const int16_t *in, int len)
 			o->squelch_hits = 0;
 		}
 	}
+	/* -L statistics input (src/rtl_fm.c:792-794): reuse the squelch's rms unless it was 0 */
+	if (o->want_levels && !o->last_level) { o->last_level = buffer_rms(o->iq, o->iq_len, 1); }
 	if (o->p.mode == 0) { fm_discriminate(o); } else { envelope_modes(o); }
 	if (o->p.mode == 4) { return; }
 	if (o->p.post_downsample > 1) { o->pcm_len = group_sum_inplace(o->pcm, o->pcm_len, o->p.post_downsample); }
@@ -453,6 +458,23 @@ long orx_fm_run(orx_fm *o, const int16_t *in, size_t n_int16, size_t chunk_int16
 		pos += len; c++;
 	}
 	return (long)w;
+}
+
+/* Per-chunk level (the `sr` of src/rtl_fm.c:792-806); same contract as ref_fm_run_levels. */
+long orx_fm_run_levels(orx_fm *o, const int16_t *in, size_t n_int16, size_t chunk_int16, int *levels)
+{
+	size_t pos = 0, c = 0;
+	if (chunk_int16 == 0 || chunk_int16 > ORX_MAX_CHUNK) { return -2; }
+	o->want_levels = 1;
+	while (pos < n_int16) {
+		size_t len = n_int16 - pos;
+		if (len > chunk_int16) { len = chunk_int16; }
+		fm_chunk(o, in + pos, (int)len);
+		levels[c] = o->last_level;
+		pos += len; c++;
+	}
+	o->want_levels = 0;
+	return (long)c;
 }
 
 double orx_fm_time(orx_fm *o, const int16_t *in, size_t n_int16, size_t chunk_int16, int repeats, long *n_out)

@@ -62,6 +62,7 @@ struct FmDev {
 	int resample, fast, slow, lpr_div;
 	int offset_tuning;
 	int squelch, rdc_on, rdc_k, adc_on, adc_k;   // per-chunk reduction stages (src/rtl_fm.c:781-790, :699-721, :684-697)
+	int levels;                                  // keep per-chunk rms() (-L, src/rtl_fm.c:792-806)
 	int fir[6];
 	const int *atan_lut;
 };
@@ -998,7 +999,7 @@ __global__ void fm_rdc_recur_kernel(const long long *sums, const int *chunk_len,
 
 // rms() + squelch decision (src/rtl_fm.c:739-757, :781-790); dec_len = decimated complex samples of the chunk
 __global__ void fm_squelch_kernel(const long long *sums, const int *dec_len, int n_chunks, int n_ch, int level,
-                                  const uint32_t *carry_in, uint32_t *carry_out, int state_words, int *sqz)
+                                  const uint32_t *carry_in, uint32_t *carry_out, int state_words, int *sqz, int *levels)
 {
 	const int ch = blockIdx.x * blockDim.x + threadIdx.x;
 	if (ch >= n_ch) { return; }
@@ -1011,9 +1012,12 @@ __global__ void fm_squelch_kernel(const long long *sums, const int *dec_len, int
 		const double dc = __ddiv_rn((double)t, (double)len);
 		const double err = __dsub_rn(__dmul_rn((double)(t * 2), dc), __dmul_rn(__dmul_rn(dc, dc), (double)len));
 		const int sr = (int)sqrt(__ddiv_rn(__dsub_rn((double)p, err), (double)len));
-		const int z = sr < level ? 1 : 0;
-		hits = z ? hits + 1 : 0;
-		sqz[(size_t)ch * n_chunks + ci] = z;
+		if (levels) { levels[(size_t)ch * n_chunks + ci] = sr; }
+		if (level) {                       // squelch off: squelch_hits is never touched (:781)
+			const int z = sr < level ? 1 : 0;
+			hits = z ? hits + 1 : 0;
+			sqz[(size_t)ch * n_chunks + ci] = z;
+		}
 	}
 	carry_out[(size_t)ch * state_words + ST_SQ_HITS] = (uint32_t)hits;
 }
@@ -1121,7 +1125,7 @@ struct rxb200_fm {
 	int wide;                      // all-scalar fifth_order passes (raw DC block on)
 	int smem_optin;
 	// per-chunk reduction stages
-	long long *d_sums; int *d_rdc, *d_sqz, *d_adc, *d_lens; size_t chunk_cap;
+	long long *d_sums; int *d_rdc, *d_sqz, *d_adc, *d_lens, *d_levels; size_t chunk_cap; int level_chunks;
 	std::vector<int> *h_lens;
 	cudaEvent_t ev0, ev1;
 };
@@ -1148,6 +1152,7 @@ static void fm_fill_dev(rxb200_fm *h)
 	memset(&d, 0, sizeof d);
 	d.mode = p.mode; d.P = p.downsample_passes; d.PL = fm_packed_levels(d.P, h->wide);
 	d.squelch = p.squelch_level; d.rdc_on = p.dc_block_raw ? 1 : 0; d.rdc_k = p.rdc_block_const;
+	d.levels = p.report_levels ? 1 : 0;
 	d.adc_on = (p.dc_block_audio && p.mode != RXB200_MODE_RAW) ? 1 : 0; d.adc_k = p.adc_block_const;
 	d.D = p.downsample_passes ? (1 << p.downsample_passes) : p.downsample;
 	d.fir_on = (p.downsample_passes > 0 && p.comp_fir_size == 9) ? 1 : 0;
@@ -1189,7 +1194,8 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	memset(h, 0, sizeof *h);
 	h->p = *params; h->device = device; h->n_channels = n_channels;
 	// any per-chunk reduction stage selects the SPEC 2 kernel (all-scalar passes + stage bookkeeping)
-	h->wide = (params->dc_block_raw || params->squelch_level || params->dc_block_audio || params->post_downsample > 1) ? 1 : 0;
+	h->wide = (params->dc_block_raw || params->squelch_level || params->dc_block_audio || params->post_downsample > 1 ||
+	           params->report_levels) ? 1 : 0;
 	h->state_words = fm_state_words(params->downsample_passes, h->wide);
 	h->h_lens = new std::vector<int>();
 	{
@@ -1252,7 +1258,7 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 	cudaStreamSynchronize(h->stream);
 	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_sync);
 	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
-	cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens);
+	cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens); cudaFree(h->d_levels);
 	delete h->h_lens;
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
@@ -1449,17 +1455,18 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		launches++;
 		return RXB200_OK;
 	};
-	if (dv.rdc_on || dv.squelch || dv.adc_on) {
+	if (dv.rdc_on || dv.squelch || dv.adc_on || dv.levels) {
 		// per-chunk scalars: sizes (closed form), accumulators, then one recurrence per stage in the
 		// reference's order: raw DC block -> squelch (sees the DC-blocked data) -> audio DC block
 		const size_t cells = (size_t)n_chunks * h->n_channels;
 		if (cells > h->chunk_cap) {
-			cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens);
-			h->d_sums = nullptr; h->d_rdc = h->d_sqz = h->d_adc = h->d_lens = nullptr; h->chunk_cap = 0;
+			cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens); cudaFree(h->d_levels);
+			h->d_sums = nullptr; h->d_rdc = h->d_sqz = h->d_adc = h->d_lens = h->d_levels = nullptr; h->chunk_cap = 0;
 			RXB_CUDA(cudaMalloc(&h->d_sums, cells * 2 * sizeof(long long)));
 			RXB_CUDA(cudaMalloc(&h->d_rdc, cells * 2 * sizeof(int)));
 			RXB_CUDA(cudaMalloc(&h->d_sqz, cells * sizeof(int)));
 			RXB_CUDA(cudaMalloc(&h->d_adc, cells * sizeof(int)));
+			RXB_CUDA(cudaMalloc(&h->d_levels, cells * sizeof(int)));
 			RXB_CUDA(cudaMalloc(&h->d_lens, (size_t)n_chunks * 3 * sizeof(int)));
 			h->chunk_cap = cells;
 		}
@@ -1488,16 +1495,17 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 			launches += 2;
 			k.rdc = h->d_rdc;
 		}
-		if (dv.squelch) {
+		if (dv.squelch || dv.levels) {
 			RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, cells * 2 * sizeof(long long), h->stream));
 			k.sums = h->d_sums;
 			int rc2 = run_fused(1);
 			if (rc2 != RXB200_OK) { return rc2; }
 			fm_squelch_kernel<<<cb, 64, 0, h->stream>>>(h->d_sums, h->d_lens + n_chunks, n_chunks, h->n_channels, dv.squelch, k.carry_in,
-			                                             k.carry_out, h->state_words, h->d_sqz);
+			                                             k.carry_out, h->state_words, h->d_sqz, dv.levels ? h->d_levels : nullptr);
 			RXB_CUDA(cudaGetLastError());
 			launches++;
-			k.sqz = h->d_sqz;
+			k.sqz = dv.squelch ? h->d_sqz : nullptr;
+			h->level_chunks = n_chunks;
 		}
 		if (dv.adc_on) {
 			RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, cells * 2 * sizeof(long long), h->stream));
@@ -1530,7 +1538,7 @@ extern "C" int rxb200_fm_process_device(rxb200_fm *h, const int16_t *d_cs16, siz
 	int rc = fm_check_shape(h, n_int16, chunk_int16);
 	if (rc != RXB200_OK) { return rc; }
 	RXB_CUDA(cudaSetDevice(h->device));
-	if (n_int16 == 0) { if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
+	if (n_int16 == 0) { h->level_chunks = 0; if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
 	size_t total = fm_count_outputs(h, n_int16, chunk_int16, nullptr, false);
 	if (total == (size_t)-1) { set_error("-o %d needs every chunk to decimate to a multiple of it", h->dev.post_ds); return RXB200_EUNSUPPORTED; }
 	if (total > pcm_stride) { set_error("pcm_stride %zu < %zu outputs", pcm_stride, total); return RXB200_ECAPACITY; }
@@ -1552,7 +1560,7 @@ extern "C" int rxb200_fm_process(rxb200_fm *h, const int16_t *cs16, size_t n_int
 	int rc = fm_check_shape(h, n_int16, chunk_int16);
 	if (rc != RXB200_OK) { return rc; }
 	RXB_CUDA(cudaSetDevice(h->device));
-	if (n_int16 == 0) { if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
+	if (n_int16 == 0) { h->level_chunks = 0; if (n_pcm) { *n_pcm = 0; } return RXB200_OK; }
 	size_t total = fm_count_outputs(h, n_int16, chunk_int16, chunk_result_len, false);
 	if (total == (size_t)-1) { set_error("-o %d needs every chunk to decimate to a multiple of it", h->dev.post_ds); return RXB200_EUNSUPPORTED; }
 	if (total > pcm_stride) { set_error("pcm_stride %zu < %zu outputs", pcm_stride, total); return RXB200_ECAPACITY; }
@@ -1593,6 +1601,20 @@ extern "C" int rxb200_fm_squelch_hits(rxb200_fm *h, int *hits)
 	RXB_CUDA(cudaMemcpyAsync(st.data(), h->d_carry[h->cur], st.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
 	RXB_CUDA(cudaStreamSynchronize(h->stream));
 	for (int c = 0; c < h->n_channels; c++) { hits[c] = (int)st[(size_t)c * h->state_words + ST_SQ_HITS]; }
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_fm_levels(rxb200_fm *h, int *levels, size_t cap, size_t *n_chunks)
+{
+	if (!h || !levels || !n_chunks) { set_error("null argument"); return RXB200_EINVAL; }
+	if (!h->p.report_levels) { set_error("handle was created without report_levels"); return RXB200_EINVAL; }
+	const size_t cells = (size_t)h->level_chunks * h->n_channels;
+	*n_chunks = (size_t)h->level_chunks;
+	if (cap < cells) { set_error("levels capacity %zu < %zu", cap, cells); return RXB200_ECAPACITY; }
+	if (!cells) { return RXB200_OK; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	RXB_CUDA(cudaMemcpyAsync(levels, h->d_levels, cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	RXB_CUDA(cudaStreamSynchronize(h->stream));
 	return RXB200_OK;
 }
 

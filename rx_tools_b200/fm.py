@@ -39,13 +39,14 @@ class FmParams:
     dc_block_raw: int = 0
     rdc_block_const: int = 9
     offset_tuning: int = 0
+    report_levels: int = 0
 
     def to_c(self) -> _lib.FmParamsC:
         return _lib.FmParamsC(*[int(getattr(self, f.name)) for f in fields(self)])
 
     @classmethod
     def from_any(cls, other) -> "FmParams":
-        return cls(**{f.name: int(getattr(other, f.name)) for f in fields(cls)})
+        return cls(**{f.name: int(getattr(other, f.name, 0)) for f in fields(cls)})
 
 
 @dataclass
@@ -120,6 +121,20 @@ class FmDemod:
         _lib.check(_lib.lib().rxb200_fm_process_device(self._h, d_in_ptr, n_int16, chunk_int16, d_out_ptr, out_stride,
                                                        C.byref(n_pcm), 1 if sync else 0))
         return int(n_pcm.value)
+
+    def levels(self) -> np.ndarray:
+        """rms() of every chunk of the last call, int32[n_channels][n_chunks] (needs report_levels;
+        the ``sr`` of src/rtl_fm.c:792-806)."""
+        cap = 1024
+        while True:
+            buf = np.zeros(cap, dtype=np.int32)
+            n = C.c_size_t(0)
+            rc = _lib.lib().rxb200_fm_levels(self._h, buf.ctypes.data_as(C.POINTER(C.c_int)), cap, C.byref(n))
+            if rc == _lib.ECAPACITY:
+                cap = int(n.value) * self.n_channels
+                continue
+            _lib.check(rc)
+            return buf[:int(n.value) * self.n_channels].reshape(self.n_channels, int(n.value)).copy()
 
     @property
     def stream(self) -> int:

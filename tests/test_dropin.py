@@ -31,7 +31,7 @@ def _run(cmd, env=None):
 
 
 def _oracle_params(p):
-    return oracle.FmParams(**p.__dict__)
+    return oracle.FmParams(**{k: v for k, v in p.__dict__.items() if k != "report_levels"})
 
 
 @pytest.mark.parametrize("args,kw", [
@@ -52,6 +52,34 @@ def test_rx_fm_output_bytes(tmp_path, port, args, kw):
     want = port.fm_run(_oracle_params(p), x, CHUNK16)
     assert got.size == want.size
     assert np.array_equal(got, want)
+
+
+def test_rx_fm_level_printing(tmp_path, port):
+    # -L N: every N chunks print mean / max / max-of-max of the chunk rms and the squelch level (src/rtl_fm.c:792-806)
+    loud = synth.cfg2_iq(3 * 131072, seed=34)
+    quiet = synth.fm_iq(4 * 131072, fs=2.4e6, deviation_hz=75e3, tones=[(1000.0, 1.0)], amplitude=900.0, noise_lsb=2, seed=35)
+    x = np.concatenate([loud, quiet])
+    cap = tmp_path / "cap.cs16"
+    x.tofile(cap)
+    out = tmp_path / "out.raw"
+    r = _run([RX_FM, "-f", "100M", "-M", "wbfm", "-s", "300k", "-F", "9", "-r", "48k", "-L", "2",
+              "-d", f"driver=file,path={cap}", str(out)])
+    p = fm.derive_params(wbfm=1, rate_s=300000, rate_r=48000, use_F=1, comp_fir_size=9).params
+    lv = port.fm_levels(_oracle_params(p), x, CHUNK16)
+    want_lines, no, lsum, lmax, lmaxmax = [], 1, 0.0, 0, 0
+    for sr in lv:
+        no -= 1
+        lsum += int(sr); lmax = max(lmax, int(sr)); lmaxmax = max(lmaxmax, int(sr))
+        if no == 0:
+            no = 2
+            want_lines.append("%f, %d, %d, %d" % (lsum / 2, lmax, lmaxmax, 0))
+            lmax, lsum = 0, 0.0
+    got_lines = [ln for ln in r.stderr.decode().splitlines() if ln.count(",") == 3 and ln[0].isdigit()]
+    assert len(want_lines) >= 3
+    assert got_lines == want_lines
+    # and the PCM is the same as without -L
+    want = port.fm_run(_oracle_params(p), x, CHUNK16)
+    assert np.array_equal(np.fromfile(out, dtype=np.int16), want)
 
 
 def test_rx_fm_wav_header_and_squelch_zero(tmp_path, port):

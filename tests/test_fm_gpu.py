@@ -137,3 +137,35 @@ def test_optional_stages(case, port):
     got = d.full_demod(x, case.chunk_int16)
     _compare(case, got, want)
     d.close()
+
+
+@pytest.mark.parametrize("case", (fm_cases() + fm_optional_cases())[::2], ids=lambda c: c.name)
+def test_levels(case, port):
+    """-L statistics input: the rms() of every chunk (src/rtl_fm.c:792-806), and the PCM is unchanged."""
+    import dataclasses
+    x = case.make_input()
+    want_pcm = port.fm_run(case.params, x, case.chunk_int16)
+    want_lv = port.fm_levels(case.params, x, case.chunk_int16)
+    p = fm.FmParams.from_any(case.params)
+    p = dataclasses.replace(p, report_levels=1)
+    d = fm.FmDemod(p)
+    got = d.full_demod(x, case.chunk_int16)
+    lv = d.levels()
+    _compare(case, got, want_pcm)
+    assert lv.shape == (1, want_lv.size)
+    assert np.array_equal(lv[0], want_lv)
+    # streaming: two calls, levels are those of the last call only
+    d.reset()
+    n_chunks = want_lv.size
+    if n_chunks >= 2:
+        cut = (n_chunks // 2) * case.chunk_int16
+        d.full_demod(x[:cut], case.chunk_int16)
+        assert np.array_equal(d.levels()[0], want_lv[:n_chunks // 2])
+        d.full_demod(x[cut:], case.chunk_int16)
+        assert np.array_equal(d.levels()[0], want_lv[n_chunks // 2:])
+    d.close()
+    # a handle without the switch refuses
+    d2 = fm.FmDemod(case.params)
+    with pytest.raises(_lib.Rxb200Error):
+        d2.levels()
+    d2.close()

@@ -40,6 +40,17 @@ def test_fm_port_equals_reference(case, port, ref_fm):
     assert np.array_equal(a, b)          # same libm, same machine: bit-exact incl. atan2 path
 
 
+@pytest.mark.parametrize("case", (fm_cases() + fm_optional_cases())[::2], ids=lambda c: c.name)
+def test_fm_levels_port_equals_reference(case, port, ref_fm):
+    # the per-chunk `sr` behind the -L statistics (src/rtl_fm.c:792-806)
+    x = case.make_input()
+    a = port.fm_levels(case.params, x, case.chunk_int16)
+    b = ref_fm.levels(case.params, x, case.chunk_int16)
+    assert a.size == b.size and a.size >= 1
+    assert np.array_equal(a, b)
+    assert b.max() > 0
+
+
 def test_derivation_matches_optimal_settings(ref_fm):
     from rx_tools_b200 import fm
     combos = [dict(rate_s=1024000, rate_r=24000), dict(wbfm=1), dict(wbfm=1, rate_s=2400000, rate_r=48000),
@@ -50,7 +61,9 @@ def test_derivation_matches_optimal_settings(ref_fm):
     for kw in combos:
         want, cap_rate, cap_off = ref_fm.derive(**kw)
         got = fm.derive_params(**kw)
-        assert dataclasses.asdict(got.params) == dataclasses.asdict(want), (kw, got.params, want)
+        mine = dataclasses.asdict(got.params)
+        assert mine.pop("report_levels") == 0          # library-only switch, not a reference field
+        assert mine == dataclasses.asdict(want), (kw, got.params, want)
         assert got.capture_rate == cap_rate and got.capture_freq_offset == cap_off, kw
 
 
