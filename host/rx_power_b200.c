@@ -4,7 +4,8 @@
  * ("date, time, Hz low, Hz high, Hz step, samples, dB, dB, ..."), same SoapySDR CS16 stream surface.
  * Host logic is our own: plan (rxb200_power_plan_range == frequency_range()), retune + flush read per
  * hop, one readStream per hop buffer; the window x fix_fft x power-accumulate of every hop of a sweep is
- * ONE rxb200_power_accumulate() call, the report is rxb200_power_read() + rxb200_power_format_row().
+ * ONE rxb200_power_accumulate() call, the report is rxb200_power_read_db() (csv_dbm's arithmetic on the
+ * device) + rxb200_power_format_db_row().
  */
 #include <math.h>
 #include <signal.h>
@@ -127,7 +128,8 @@ int main(int argc, char **argv)
 	int16_t *rd = (int16_t *)malloc((size_t)buf_len * 4);
 	int16_t *dump = (int16_t *)malloc((size_t)BUFFER_DUMP * 4);
 	int16_t *stage = (int16_t *)malloc((size_t)n_hops * (size_t)buf_len * 2);
-	int64_t *avg = (int64_t *)malloc((size_t)n_hops * (size_t)N * sizeof(int64_t));
+	const int row_len = rxb200_power_row_len(pp->bin_e, plan.crop);
+	double *db = (double *)malloc((size_t)n_hops * (size_t)row_len * sizeof(double));
 	int *samples = (int *)malloc((size_t)n_hops * sizeof(int));
 	char *row = (char *)malloc(64 + 16 * ((size_t)N + 8));
 	const char *hook = getenv("RXB200_MAX_SWEEPS");       /* test hook: report after this many sweeps and exit */
@@ -180,12 +182,12 @@ int main(int argc, char **argv)
 		localtime_r(&now, &cal);
 		strftime(tstr, sizeof tstr, "%Y-%m-%d, %H:%M:%S", &cal);
 		if (getenv("RXB200_FIXED_TIME")) { snprintf(tstr, sizeof tstr, "%s", getenv("RXB200_FIXED_TIME")); }
-		if (rxb200_power_read(pw, avg, samples) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); break; }
+		if (rxb200_power_read_db(pw, plan.rate, plan.crop, db, (size_t)row_len, samples) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); break; }
 		int have = 0;
 		for (int i = 0; i < n_hops; i++) { have |= samples[i]; }
 		if (have) {
 			for (int i = 0; i < n_hops; i++) {
-				int n = rxb200_power_format_row(avg + (size_t)i * N, pp->bin_e, plan.first_freq + (int64_t)i * plan.freq_step, plan.rate,
+				int n = rxb200_power_format_db_row(db + (size_t)i * row_len, pp->bin_e, plan.first_freq + (int64_t)i * plan.freq_step, plan.rate,
 				                                pp->downsample, plan.crop, samples[i], row, 64 + 16 * ((size_t)N + 8));
 				if (n < 0) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); break; }
 				fprintf(out, "%s, ", tstr);

@@ -238,6 +238,17 @@ int rxb200_power_last_launches(rxb200_power *h);
 /* Device time of the batched kernel alone in the last accumulate call (ms); synchronises. */
 int rxb200_power_kernel_ms(rxb200_power *h, float *ms);
 
+/* csv_dbm()'s numeric half ON THE DEVICE (src/rtl_power.c:783-811): DC-bin patch, half swap, crop and
+ * power -> dB in the reference's fp64 operation order, so that only the final dB values leave the GPU.
+ * db receives [n_hops][row_len] doubles, row_len = kept bins + 1 (the reference prints the last bin
+ * twice, :807-811); rows are row_stride doubles apart.  The accumulators are NOT modified (call
+ * rxb200_power_reset for csv_dbm's zeroing, :813-816).  RXB200_ECAPACITY if row_stride < row_len. */
+int rxb200_power_row_len(int bin_e, double crop);
+int rxb200_power_read_db(rxb200_power *h, int rate, double crop, double *db, size_t row_stride, int *samples);
+/* The text half: same line as rxb200_power_format_row from one row of rxb200_power_read_db. */
+int rxb200_power_format_db_row(const double *db_row, int bin_e, int64_t freq, int rate, int downsample,
+                               double crop, int samples, char *dst, size_t cap);
+
 /* csv_dbm() (src/rtl_power.c:774-817) for one hop row on the host: formats
  * "Hz low, Hz high, Hz step, samples, dB, dB, ...\n" into dst (the caller prints the date/time
  * prefix, :1048).  avg_row (N int64) is modified like the reference does (DC nuke + fft-shift).

@@ -61,7 +61,8 @@ SYMBOLS = [
     "rxb200_power_plan_range", "rxb200_window_table", "rxb200_sine_table", "rxb200_power_create",
     "rxb200_power_destroy", "rxb200_power_accumulate", "rxb200_power_accumulate_device", "rxb200_power_read",
     "rxb200_power_device_avg", "rxb200_power_reset", "rxb200_power_stream", "rxb200_power_last_launches",
-    "rxb200_power_format_row", "rxb200_power_kernel_ms",
+    "rxb200_power_format_row", "rxb200_power_kernel_ms", "rxb200_power_row_len", "rxb200_power_read_db",
+    "rxb200_power_format_db_row",
     "rxb200_sdr_convert", "rxb200_sdr_convert_device",
 ]
 
@@ -113,6 +114,10 @@ def lib() -> C.CDLL:
     L.rxb200_power_last_launches.argtypes = [C.c_void_p]
     L.rxb200_power_format_row.argtypes = [pi64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                           C.c_char_p, sz]
+    L.rxb200_power_row_len.argtypes = [C.c_int, C.c_double]
+    L.rxb200_power_read_db.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), sz, pint]
+    L.rxb200_power_format_db_row.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                             C.c_int, C.c_char_p, sz]
     L.rxb200_sdr_convert.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_int]
     L.rxb200_sdr_convert_device.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     _lib = L

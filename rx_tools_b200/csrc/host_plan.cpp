@@ -191,6 +191,38 @@ extern "C" int rxb200_sine_table(int log2_n, int16_t *sine)
 
 // csv_dbm() (src/rtl_power.c:774-817) for one row, without the date/time prefix and without the
 // zeroing (the device accumulators are cleared by rxb200_power_reset).
+extern "C" int rxb200_power_row_len(int bin_e, double crop)
+{
+	if (bin_e < 0 || bin_e > 30) { return RXB200_EINVAL; }
+	const int len = 1 << bin_e;
+	const int i1 = 0 + (int)((double)len * crop * 0.5);
+	const int i2 = (len - 1) - (int)((double)len * crop * 0.5);
+	return (i2 >= i1 ? i2 - i1 + 1 : 0) + 1;
+}
+
+extern "C" int rxb200_power_format_db_row(const double *db, int bin_e, int64_t freq, int rate, int downsample,
+                                          double crop, int samples, char *dst, size_t cap)
+{
+	if (!db || !dst) { set_error("null argument"); return RXB200_EINVAL; }
+	const int len = 1 << bin_e, ds = downsample;
+	const int n = rxb200_power_row_len(bin_e, crop);
+	size_t w = 0;
+#define RXB_EMIT(...)                                                        \
+	do {                                                                     \
+		int n__ = snprintf(dst + w, w < cap ? cap - w : 0, __VA_ARGS__);     \
+		if (n__ < 0 || w + (size_t)n__ >= cap) { return RXB200_ECAPACITY; }  \
+		w += (size_t)n__;                                                    \
+	} while (0)
+	int bin_count = (int)((double)len * (1.0 - crop));
+	int bw2 = (int)(((double)rate * (double)bin_count) / (len * 2 * ds));
+	RXB_EMIT("%lli, %lli, %.2f, %i, ", (long long)freq - bw2, (long long)freq + bw2,
+	         (double)rate / (double)(len * ds), samples);
+	for (int i = 0; i < n - 1; i++) { RXB_EMIT("%.2f, ", db[i]); }
+	RXB_EMIT("%.2f\n", db[n - 1]);
+#undef RXB_EMIT
+	return (int)w;
+}
+
 extern "C" int rxb200_power_format_row(int64_t *avg, int bin_e, int64_t freq, int rate, int downsample,
                                        double crop, int samples, char *dst, size_t cap)
 {

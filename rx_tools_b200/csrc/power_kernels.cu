@@ -590,6 +590,7 @@ struct rxb200_power {
 	int launches;
 	int n_sm;
 	cudaEvent_t ev0, ev1;
+	void *d_db = nullptr; size_t db_cap = 0;   // csv_dbm staging (rxb200_power_read_db)
 };
 
 static int power_validate(const rxb200_power_params *p)
@@ -656,7 +657,7 @@ extern "C" void rxb200_power_destroy(rxb200_power *h)
 	if (!h) { return; }
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	cudaFree(h->d_avg); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in);
+	cudaFree(h->d_avg); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_db);
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -793,6 +794,64 @@ extern "C" int rxb200_power_read(rxb200_power *h, int64_t *avg, int *samples)
 		const size_t N = (size_t)1 << h->p.bin_e;
 		RXB_CUDA(cudaMemcpyAsync(avg, h->d_avg, (size_t)h->p.n_hops * N * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
 	}
+	RXB_CUDA(cudaStreamSynchronize(h->stream));
+	if (samples) { memcpy(samples, h->samples.data(), h->samples.size() * sizeof(int)); }
+	return RXB200_OK;
+}
+
+// csv_dbm's arithmetic (src/rtl_power.c:783-811) without touching avg: element i of the patched and
+// half-swapped row is avg0[(i + N/2) mod N] with avg0[0] := avg[1]; every kept bin goes through
+// /rate, /samples, 10*log10 in that order; the trailing value divides by (rate*samples) at once.
+__global__ void power_db_kernel(const long long *avg, const int *samples, int n_hops, int bin_e, int i1, int row_len,
+                                double rate, double *db, size_t row_stride)
+{
+	const int hop = blockIdx.y;
+	const int N = 1 << bin_e;
+	const long long *row = avg + (size_t)hop * N;
+	const double smp = (double)samples[hop];
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += gridDim.x * blockDim.x) {
+		const bool last = (j == row_len - 1);
+		int i = last ? i1 + row_len - 2 : i1 + j;          // the last kept bin is printed twice (:807)
+		if (bin_e == 0) { i = 0; }
+		long long v;
+		if (bin_e > 0) {
+			int src = (i + N / 2) & (N - 1);
+			if (src == 0) { src = 1; }                      // avg[0] = avg[1] (:784)
+			v = row[src];
+		} else {
+			v = row[0];
+		}
+		double d;
+		if (last) { d = __ddiv_rn((double)v, __dmul_rn(rate, smp)); }
+		else      { d = __ddiv_rn(__ddiv_rn((double)v, rate), smp); }
+		db[(size_t)hop * row_stride + j] = __dmul_rn(10.0, log10(d));
+	}
+}
+
+extern "C" int rxb200_power_read_db(rxb200_power *h, int rate, double crop, double *db, size_t row_stride, int *samples)
+{
+	if (!h || !db) { set_error("null argument"); return RXB200_EINVAL; }
+	const int row_len = rxb200_power_row_len(h->p.bin_e, crop);
+	if (row_len < 2 && h->p.bin_e > 0) { set_error("crop %f leaves no bins", crop); return RXB200_EINVAL; }
+	if (row_stride < (size_t)row_len) { set_error("row_stride %zu < row_len %d", row_stride, row_len); return RXB200_ECAPACITY; }
+	RXB_CUDA(cudaSetDevice(h->device));
+	const int n_hops = h->p.n_hops;
+	const size_t need = (size_t)n_hops * row_len * sizeof(double) + (size_t)n_hops * sizeof(int);
+	if (need > h->db_cap) {
+		cudaFree(h->d_db); h->d_db = nullptr; h->db_cap = 0;
+		RXB_CUDA(cudaMalloc(&h->d_db, need));
+		h->db_cap = need;
+	}
+	double *d_db = reinterpret_cast<double *>(h->d_db);
+	int *d_smp = reinterpret_cast<int *>(d_db + (size_t)n_hops * row_len);
+	RXB_CUDA(cudaMemcpyAsync(d_smp, h->samples.data(), (size_t)n_hops * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	const int len = 1 << h->p.bin_e;
+	const int i1 = (int)((double)len * crop * 0.5);
+	dim3 grid((unsigned)((row_len + 255) / 256 > 64 ? 64 : (row_len + 255) / 256), (unsigned)n_hops);
+	power_db_kernel<<<grid, 256, 0, h->stream>>>(h->d_avg, d_smp, n_hops, h->p.bin_e, i1, row_len, (double)rate, d_db, (size_t)row_len);
+	RXB_CUDA(cudaGetLastError());
+	RXB_CUDA(cudaMemcpy2DAsync(db, row_stride * sizeof(double), d_db, (size_t)row_len * sizeof(double),
+	                           (size_t)row_len * sizeof(double), (size_t)n_hops, cudaMemcpyDeviceToHost, h->stream));
 	RXB_CUDA(cudaStreamSynchronize(h->stream));
 	if (samples) { memcpy(samples, h->samples.data(), h->samples.size() * sizeof(int)); }
 	return RXB200_OK;

@@ -116,6 +116,29 @@ class PowerScanner:
                                                 samples.ctypes.data_as(C.POINTER(C.c_int))))
         return avg, samples
 
+    def read_db(self):
+        """csv_dbm's numbers computed on the device (src/rtl_power.c:783-811): float64[n_hops][row_len], samples."""
+        row_len = _lib.check(_lib.lib().rxb200_power_row_len(self.plan.bin_e, self.plan.crop))
+        db = np.zeros((self.plan.n_hops, row_len), dtype=np.float64)
+        samples = np.zeros(self.plan.n_hops, dtype=np.int32)
+        _lib.check(_lib.lib().rxb200_power_read_db(self._h, self.plan.rate, self.plan.crop,
+                                                   db.ctypes.data_as(C.POINTER(C.c_double)), row_len,
+                                                   samples.ctypes.data_as(C.POINTER(C.c_int))))
+        return db, samples
+
+    def csv_rows_device(self, tstr: str = "2026-01-01, 00:00:00") -> str:
+        """The CSV text of csv_dbm() over every hop with the dB values computed on the device."""
+        db, samples = self.read_db()
+        buf = C.create_string_buffer(64 + 16 * (db.shape[1] + 8))
+        lines = []
+        for i in range(self.plan.n_hops):
+            row = np.ascontiguousarray(db[i])
+            r = _lib.check(_lib.lib().rxb200_power_format_db_row(row.ctypes.data_as(C.POINTER(C.c_double)), self.plan.bin_e,
+                                                                 self.plan.hop_freq(i), self.plan.rate, self.plan.downsample,
+                                                                 self.plan.crop, int(samples[i]), buf, len(buf)))
+            lines.append(tstr + ", " + buf.raw[:r].decode())
+        return "".join(lines)
+
     def reset(self) -> None:
         _lib.check(_lib.lib().rxb200_power_reset(self._h))
 

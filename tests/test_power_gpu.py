@@ -110,3 +110,41 @@ def test_every_fft_size(bin_e, peak, port):
     bad = np.argwhere(avg != want)
     assert bad.size == 0, (bin_e, bad[:4])
     sc.close()
+
+
+@pytest.mark.parametrize("case", power_cases(), ids=lambda c: c.name)
+def test_csv_dbm_on_device(case, port):
+    """csv_dbm's arithmetic on the device (src/rtl_power.c:783-811): the CSV text equals the host formatter's
+    (which tests/test_host_logic.py pins against the reference's own csv_dbm), and the accumulators stay intact."""
+    plan = power.plan_range(case.freq_arg, case.crop, case.boxcar, case.comp_fir_size, case.peak_hold)
+    win = power.window_table(case.window, 1 << plan.bin_e)
+    x = power_input(case, plan.n_hops, plan.buf_len)
+    try:
+        sc = power.PowerScanner(plan, win)
+    except _lib.Rxb200Error as e:
+        assert e.code == _lib.EUNSUPPORTED
+        pytest.skip("shape not supported")
+    sc.scanner(x, case.n_pass)
+    avg, smp = sc.read()
+    text_dev = sc.csv_rows_device()
+    text_host = power.csv_rows(plan, avg, smp)
+    assert text_dev == text_host
+    assert text_dev.count("\n") == plan.n_hops
+    avg2, _ = sc.read()
+    assert np.array_equal(avg, avg2)
+    # the doubles themselves: same operation order as C, log10 within 1 ulp of the host's
+    db, smp2 = sc.read_db()
+    n = 1 << plan.bin_e
+    a = avg.astype(np.int64).copy()
+    if plan.bin_e > 0:
+        a[:, 0] = a[:, 1]
+        a = np.roll(a, n // 2, axis=1)
+    i1 = int(n * plan.crop * 0.5)
+    i2 = (n - 1) - int(n * plan.crop * 0.5)
+    with np.errstate(divide="ignore"):
+        want = 10 * np.log10(a[:, i1:i2 + 1].astype(np.float64) / float(plan.rate) / smp[:, None].astype(np.float64))
+    assert db.shape == (plan.n_hops, i2 - i1 + 2)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(db[:, :-1]), fin)
+    assert np.allclose(db[:, :-1][fin], want[fin], rtol=0, atol=1e-12)
+    sc.close()
