@@ -422,7 +422,7 @@ def _cpu_worker(job):
     from rx_tools_b200 import fm, power, synth  # host-side derivation only (no GPU use)
     if workload.startswith("fm"):
         p = fm_params(workload)
-        op = oracle.FmParams(**p.__dict__)
+        op = oracle.FmParams(**p.reference_fields())
         x = fm_input_period(workload, n_complex)
         if kind_pref == "reference" and oracle.have_ref():
             t = oracle.RefFm().time(op, x, CHUNK, repeats)

@@ -49,6 +49,27 @@ namespace rxb {
 #ifndef RXB_OCC
 #define RXB_OCC 3
 #endif
+#ifndef RXB_RCP_APPROX
+#define RXB_RCP_APPROX 1     // fast_atan2: bare MUFU.RCP (the +-1 remainder correction absorbs its 1 ulp)
+#endif
+#ifndef RXB_CHUNK_VOTE
+#define RXB_CHUNK_VOTE 1     // chunk-start bookkeeping behind a warp vote instead of 16 predicated moves per block
+#endif
+#ifndef RXB_FIR_PACKED
+#define RXB_FIR_PACKED 1     // droop FIR on biased packed history: symmetric taps added two lanes at a time
+#endif
+#ifndef RXB_LOAD_INPLACE
+#define RXB_LOAD_INPLACE 1   // packed passes: next block is loaded into the registers the scale just freed
+#endif
+#ifndef RXB_L0_UNBIASED
+#define RXB_L0_UNBIASED 0    // 1: pass-0 lanes stay signed (q*65536 + i), bias added once per tap; measured 2 % SLOWER on B200
+#endif
+#ifndef RXB_BE_QUADS
+#define RXB_BE_QUADS 1       // back-end replay walks 4-aligned quads of the PCM buffer (one address per 4 samples)
+#endif
+#ifndef RXB_MAIN_UNROLL
+#define RXB_MAIN_UNROLL 1
+#endif
 #ifndef RXB_ATAN_V
 #define RXB_ATAN_V 1
 #endif
@@ -64,6 +85,7 @@ struct FmDev {
 	int squelch, rdc_on, rdc_k, adc_on, adc_k;   // per-chunk reduction stages (src/rtl_fm.c:781-790, :699-721, :684-697)
 	int levels;                                  // keep per-chunk rms() (-L, src/rtl_fm.c:792-806)
 	int fir[6];
+	int fir_bias;                                // packed droop FIR: FIR_B * (2(c1+c2+c3+c4)+c5), see droop9_packed
 	const int *atan_lut;
 };
 
@@ -95,6 +117,7 @@ struct FmCall {
 	long long *sums;          // [..][2] accumulators of the reduction pre-passes
 	int n_chunks;
 	int reduce_mode;          // 0 main pass, 1 squelch sums (t, p), 2 audio-DC sums
+	int one;                  // always 1 (see front_run)
 };
 
 enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC, ST_LPR_PHASE,
@@ -103,6 +126,11 @@ enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC,
 static inline int fm_packed_levels(int P, int wide) { return wide ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED); }
 static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
 
+constexpr uint32_t L0_BIAS = RXB_L0_UNBIASED ? 0x00800080u : 0u;   // pass-0 lanes are unbiased in registers; carry words keep the biased format
+constexpr unsigned FIR_B = 16384u;
+// raw int16 lanes <-> lanes biased by FIR_B (no carry between lanes while |v| <= 16383)
+__device__ __forceinline__ uint32_t fir_bias_lanes(uint32_t w) { return (w ^ 0x80008000u) - 0x40004000u; }
+__device__ __forceinline__ uint32_t fir_unbias_lanes(uint32_t w) { return (w + 0x40004000u) ^ 0x80008000u; }
 __device__ __forceinline__ uint32_t pack2(int i, int q) { return ((uint32_t)i & 0xffffu) | ((uint32_t)q << 16); }
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16); }
@@ -114,6 +142,9 @@ struct FrontState {
 	// block) -> every pass is scalar
 	static constexpr int PL = (SPEC == 2) ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED);
 	static constexpr int PS = P - PL;
+	// droop FIR history kept biased (lane = v + FIR_B) when |v| <= 128 << P leaves head-room for the
+	// sum of two lanes: P <= 6 and no raw DC block
+	static constexpr bool FIRB = (RXB_FIR_PACKED != 0) && (SPEC != 2) && (P >= 1) && (P <= 6);
 	int box_i, box_q, box_n;
 	// packed passes: the last six samples the pass has seen (oldest first), I in the low and Q in
 	// the high half-word, each biased by 128<<level so both lanes stay unsigned
@@ -131,7 +162,7 @@ __device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 #pragma unroll
 	for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l); }
+		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l) - (l == 0 ? L0_BIAS : 0u); }
 	}
 #pragma unroll
 	for (int l = 0; l < FrontState<P, SPEC>::PS; l++) {
@@ -140,7 +171,7 @@ __device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 		s.pi[l] = 0; s.pq[l] = 0;
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { s.fh[j] = 0u; }
+	for (int j = 0; j < 9; j++) { s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(0u) : 0u; }
 	s.pre_i = s.pre_q = 0;
 }
 
@@ -153,7 +184,7 @@ __device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_
 #pragma unroll
 	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { s.h[l][j] = g[ST_HDR + 6 * l + j]; }
+		for (int j = 0; j < 6; j++) { s.h[l][j] = g[ST_HDR + 6 * l + j] - (l == 0 ? L0_BIAS : 0u); }
 	}
 #pragma unroll
 	for (int l = 0; l < PS; l++) {
@@ -162,7 +193,7 @@ __device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_
 		uint32_t w = g[ST_HDR + 6 * PL + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { s.fh[j] = g[ST_HDR + 6 * PL + 7 * PS + j]; }
+	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * PS + j]; s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(w) : w; }
 }
 
 template <int P, int SPEC>
@@ -174,7 +205,7 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 #pragma unroll
 	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * l + j] = s.h[l][j]; }
+		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * l + j] = s.h[l][j] + (l == 0 ? L0_BIAS : 0u); }
 	}
 #pragma unroll
 	for (int l = 0; l < PS; l++) {
@@ -183,7 +214,7 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 		g[ST_HDR + 6 * PL + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = s.fh[j]; }
+	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = FrontState<P, SPEC>::FIRB ? fir_unbias_lanes(s.fh[j]) : s.fh[j]; }
 }
 
 // ------------------------------------------------------------------------------ stages
@@ -195,6 +226,19 @@ __device__ __forceinline__ uint32_t hb_tap(uint32_t a, uint32_t b, uint32_t c, u
 {
 	uint32_t s = a + f + (b + e) * 5u + (c + d) * 10u;
 	return (s >> 4) & 0x0FFF0FFFu;
+}
+
+// Pass 0 on unbiased lanes w = q * 65536 + i: the weighted sum of such words is Q * 65536 + I with the
+// true signed lane sums, so adding the whole bias 32 * (128 | 128 << 16) once gives the same word
+// hb_tap builds from biased inputs.
+__device__ __forceinline__ uint32_t hb_tap0(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f)
+{
+#if RXB_L0_UNBIASED
+	uint32_t s = a + f + 32u * 0x00800080u + (b + e) * 5u + (c + d) * 10u;
+	return (s >> 4) & 0x0FFF0FFFu;
+#else
+	return hb_tap(a, b, c, d, e, f);
+#endif
 }
 
 // Scalar fifth_order pass for levels >= 3 (values may exceed the packed head-room; int16 wrap kept).
@@ -246,6 +290,25 @@ __device__ __forceinline__ void droop9(uint32_t (&h)[9], const int (&c)[6], int 
 	dq = wrap16(aq >> 15);
 }
 
+// Same filter on the biased history (lanes = v + FIR_B): the symmetric taps are added two lanes at a
+// time (lane sums <= 2 (FIR_B + 8192) < 65536, no carry), the bias leaves through one constant,
+//   sum c_k (v_k + v_k' + 2 FIR_B) = sum c_k (v_k + v_k') + fir_bias   (all in wrapping int32).
+__device__ __forceinline__ void droop9_packed(uint32_t (&h)[9], const int (&c)[6], int fir_bias, int &di, int &dq)
+{
+	const uint32_t s0 = h[0] + h[8], s1 = h[1] + h[7], s2 = h[2] + h[6], s3 = h[3] + h[5], s4 = h[4];
+	int ai = sub_w(mul_w((int)(s0 & 0xffffu), c[1]), fir_bias);
+	int aq = sub_w(mul_w((int)(s0 >> 16), c[1]), fir_bias);
+	ai = add_w(ai, mul_w((int)(s1 & 0xffffu), c[2])); aq = add_w(aq, mul_w((int)(s1 >> 16), c[2]));
+	ai = add_w(ai, mul_w((int)(s2 & 0xffffu), c[3])); aq = add_w(aq, mul_w((int)(s2 >> 16), c[3]));
+	ai = add_w(ai, mul_w((int)(s3 & 0xffffu), c[4])); aq = add_w(aq, mul_w((int)(s3 >> 16), c[4]));
+	ai = add_w(ai, mul_w((int)(s4 & 0xffffu), c[5])); aq = add_w(aq, mul_w((int)(s4 >> 16), c[5]));
+#pragma unroll
+	for (int j = 0; j < 8; j++) { h[j] = h[j + 1]; }
+	h[8] = ((uint32_t)dq << 16) + (uint32_t)di + (FIR_B * 0x10001u);
+	di = wrap16(ai >> 15);
+	dq = wrap16(aq >> 15);
+}
+
 // polar_discriminant (src/rtl_fm.c:476-483); note 3.14159.
 __device__ __noinline__ int disc_std(int cr, int cj)
 {
@@ -259,6 +322,16 @@ __device__ __noinline__ int disc_std(int cr, int cj)
 // after wrap-around of the numerator), so one fp32 reciprocal estimate plus an exact integer remainder
 // correction reproduces C's truncating '/'.  A non-positive divisor (only reachable through int32
 // overflow, or x == y == 0) takes the generic path.
+__device__ __forceinline__ float rcp_est(float x)
+{
+#if RXB_RCP_APPROX
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // <= 1 ulp; the quotient estimate stays within +-1
+	return r;
+#else
+	return __frcp_rn(x);
+#endif
+}
 __device__ __forceinline__ int fast_atan2_i(int y, int x)
 {
 #if RXB_ATAN_V == 0
@@ -277,7 +350,7 @@ __device__ __forceinline__ int fast_atan2_i(int y, int x)
 	const int den = xneg ? sub_w(ya, x) : add_w(x, ya);
 	int q;
 	if (den > 0) {
-		q = __float2int_rz(__int2float_rn(num) * __frcp_rn(__int2float_rn(den)));
+		q = __float2int_rz(__int2float_rn(num) * rcp_est(__int2float_rn(den)));
 		const int r = sub_w(num, mul_w(q, den));
 		const int up = num >= 0 ? (r >= den ? 1 : 0) : (r > 0 ? 1 : 0);
 		const int dn = num >= 0 ? (r < 0 ? 1 : 0) : (r <= -den ? 1 : 0);
@@ -390,7 +463,9 @@ struct EmitCtx {
 template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int di, int dq)
 {
-	if (c.fir_on) { droop9(s.fh, c.fir, di, dq); }
+	if (c.fir_on) {
+		if constexpr (FrontState<P, SPEC>::FIRB) { droop9_packed(s.fh, c.fir, c.fir_bias, di, dq); } else { droop9(s.fh, c.fir, di, dq); }
+	}
 	if (SPEC == 2) {
 		if (k.reduce_mode == 1) {       // rms() inputs of this chunk (src/rtl_fm.c:746-751)
 			if (STORE) { e.red_t += di + dq; e.red_p += (long long)di * di + (long long)dq * dq; }
@@ -455,7 +530,11 @@ __device__ __forceinline__ uint32_t scale_rot_pack(uint32_t w, int pos, bool rot
 {
 	int ri, rq;
 	scale_rot(w, pos, rotate, ri, rq);
+#if RXB_L0_UNBIASED
+	return (uint32_t)ri + ((uint32_t)rq << 16);          // == rq * 65536 + ri: linear, so the tap sum is too
+#else
 	return (uint32_t)(ri + 128) + ((uint32_t)(rq + 128) << 16);
+#endif
 }
 
 __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
@@ -465,45 +544,19 @@ __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
 	             : "l"(p));
 }
 
-// One block of 8 input samples at in-chunk offset u (multiple of 8).
+// The packed passes (levels < PL) of one block whose samples are already scaled, rotated and packed.
 template <int P, int SPEC, bool STORE>
-__device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
-                                            const uint32_t (&v)[8], unsigned u)
+__device__ __forceinline__ void front_block_packed(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
+                                                   const uint32_t (&x)[8], unsigned u)
 {
 	constexpr int PL = FrontState<P, SPEC>::PL;
-	const bool rot = Spec<SPEC>::rotate(c);
-	if constexpr (P == 0) {
-		// low_pass boxcar (src/rtl_fm.c:351-371)
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			int xi, xq;
-			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
-			s.box_i += xi; s.box_q += xq;
-			if (++s.box_n >= c.D) {
-				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
-				s.box_i = 0; s.box_q = 0; s.box_n = 0;
-				post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
-			}
-		}
-	} else if constexpr (PL == 0) {
-		// "wide" variant: every fifth_order pass scalar with the reference's int16 wrap
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			int xi, xq, oi, oq;
-			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
-			if (scalar_push<0, P, SPEC>(s, xi, xq, u + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
-		}
-	} else {
-		uint32_t x[8];
-#pragma unroll
-		for (int j = 0; j < 8; j++) { x[j] = scale_rot_pack(v[j], j, rot); }
 		// pass 0: window for the sample at block offset 2j is s[2j-5 .. 2j] of (h[0] .. , x[0..7])
 		uint32_t (&h0)[6] = s.h[0];
 		uint32_t y[4];
-		y[0] = hb_tap(h0[1], h0[2], h0[3], h0[4], h0[5], x[0]);
-		y[1] = hb_tap(h0[3], h0[4], h0[5], x[0], x[1], x[2]);
-		y[2] = hb_tap(h0[5], x[0], x[1], x[2], x[3], x[4]);
-		y[3] = hb_tap(x[1], x[2], x[3], x[4], x[5], x[6]);
+		y[0] = hb_tap0(h0[1], h0[2], h0[3], h0[4], h0[5], x[0]);
+		y[1] = hb_tap0(h0[3], h0[4], h0[5], x[0], x[1], x[2]);
+		y[2] = hb_tap0(h0[5], x[0], x[1], x[2], x[3], x[4]);
+		y[3] = hb_tap0(x[1], x[2], x[3], x[4], x[5], x[6]);
 #pragma unroll
 		for (int j = 0; j < 6; j++) { h0[j] = x[j + 2]; }
 		uint32_t outw[4];
@@ -541,6 +594,41 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 			}
 		}
 	}
+
+// One block of 8 input samples at in-chunk offset u (multiple of 8).
+template <int P, int SPEC, bool STORE>
+__device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
+                                            const uint32_t (&v)[8], unsigned u)
+{
+	constexpr int PL = FrontState<P, SPEC>::PL;
+	const bool rot = Spec<SPEC>::rotate(c);
+	if constexpr (P == 0) {
+		// low_pass boxcar (src/rtl_fm.c:351-371)
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int xi, xq;
+			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
+			s.box_i += xi; s.box_q += xq;
+			if (++s.box_n >= c.D) {
+				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
+				s.box_i = 0; s.box_q = 0; s.box_n = 0;
+				post_decim<P, SPEC, STORE>(c, k, s, e, di, dq);
+			}
+		}
+	} else if constexpr (PL == 0) {
+		// "wide" variant: every fifth_order pass scalar with the reference's int16 wrap
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int xi, xq, oi, oq;
+			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
+			if (scalar_push<0, P, SPEC>(s, xi, xq, u + (unsigned)j, oi, oq)) { post_decim<P, SPEC, STORE>(c, k, s, e, oi, oq); }
+		}
+	} else {
+		uint32_t x[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) { x[j] = scale_rot_pack(v[j], j, rot); }
+		front_block_packed<P, SPEC, STORE>(c, k, s, e, x, u);
+	}
 }
 
 // ------------------------------------------------------------------------------ back end
@@ -576,8 +664,30 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 	if (m >= m_end) { return; }
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
-	int x = pcm_load(pcm_s, m);
 	if (c.a_use_magic) {
+#if RXB_BE_QUADS
+		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
+		for (; (m & 3) != 0 && m < m_end; m++) {
+			const int x = pcm_load(pcm_s, m);
+			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
+			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+		}
+#pragma unroll 2
+		for (; m + 4 <= m_end; m += 4) {
+			const int16_t *q = pcm_s + pcm_phys(m);
+			const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
+			lo = deemph_fast<EVEN>(lo, x0, x0 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x0, x0 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x1, x1 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x1, x1 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x2, x2 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x2, x2 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x3, x3 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x3, x3 + bias, magic, K);
+		}
+		for (; m < m_end; m++) {
+			const int x = pcm_load(pcm_s, m);
+			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
+			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+		}
+#else
+		int x = pcm_load(pcm_s, m);
 #pragma unroll 4
 		for (; m < m_end; m++) {
 			int xn = pcm_load(pcm_s, m + 1 < m_end ? m + 1 : m);
@@ -586,9 +696,10 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 			hi = deemph_fast<EVEN>(hi, x, xb, magic, K);
 			x = xn;
 		}
+#endif
 	} else {
 		for (; m < m_end; m++) {
-			x = pcm_load(pcm_s, m);
+			const int x = pcm_load(pcm_s, m);
 			lo = deemph_step(c, lo, x);
 			hi = deemph_step(c, hi, x);
 		}
@@ -681,17 +792,43 @@ __device__ __forceinline__ void chunk_enter(const FmDev &c, const FmCall &k, Emi
 	if (c.post_ds > 1) { e.pds_acc = 0; e.pds_cnt = 0; }       // groups never span chunks
 }
 
+// chunk start inside front_run: every pass forgets the odd sample it was holding
+template <int P, int SPEC, bool STORE>
+__device__ __forceinline__ void front_chunk_start(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int ch)
+{
+	e.first_in_chunk = 1;
+	if (SPEC == 2) { chunk_enter<STORE>(c, k, e, ch, e.chunk_idx + 1); }
+#pragma unroll
+	for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
+#pragma unroll
+		for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
+	}
+}
+
+__device__ __forceinline__ void ldg256_after(const int16_t *p, uint32_t (&v)[8], uint32_t dep)
+{
+	// `dep` is not used by the instruction: it only orders the load behind the value's producer
+	asm volatile("ld.global.nc.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+	             : "l"(p), "r"(dep));
+}
+
 template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e,
                                           const int16_t *__restrict__ in, int t, int t_end, int t_last, unsigned &u, int ch)
 {
 	if (t >= t_end) { return; }
+	constexpr bool INPLACE = (RXB_LOAD_INPLACE != 0) && (FrontState<P, SPEC>::PL > 0);
 	uint32_t v[8], vn[8];
 	ldg256(in + 2 * (size_t)t, v);
+#if RXB_MAIN_UNROLL == 2
+#pragma unroll 2
+#elif RXB_MAIN_UNROLL == 3
+#pragma unroll 3
+#endif
 	for (; t < t_end; t += 8) {
-		// fetch the next block (clamped to the segment's last block) while this one is processed
-		const int tn = t + 8 <= t_last ? t + 8 : t_last;
-		ldg256(in + 2 * (size_t)tn, vn);
+		const int tn = t + 8 <= t_last ? t + 8 : t_last;       // next block, clamped to the segment's last one
+		if constexpr (!INPLACE) { ldg256(in + 2 * (size_t)tn, vn); }
 #if RXB_L2_AHEAD > 0
 		// pull the stream into L2 well ahead of the register prefetch (each thread walks its own region)
 		if ((t & RXB_L2_MASK) == 0) {
@@ -700,38 +837,37 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		}
 #endif
 		if (u >= (unsigned)k.chunk) { u = 0u; }
+#if RXB_CHUNK_VOTE
+		// a lane meets a chunk start once in chunk/8 blocks.  Left alone, ptxas if-converts the bookkeeping into
+		// ~16 predicated-off moves in EVERY block; a loop (trip count k.one == 1, unknown to the compiler) cannot
+		// be predicated, so the common path pays one branch
 		if (u == 0u) {
-			e.first_in_chunk = 1;
-			if (SPEC == 2) { chunk_enter<STORE>(c, k, e, ch, e.chunk_idx + 1); }
-			// chunk start: every pass forgets the odd sample it was holding
-#if RXB_CHUNK_BRANCH
-			if (true) {
-#pragma unroll
-				for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
-#pragma unroll
-					for (int j = 5; j > 0; j--) { s.h[l][j] = s.h[l][j - 1]; }
-				}
-			}
-#endif
+#pragma unroll 1
+			for (int z = 0; z < k.one; z++) { front_chunk_start<P, SPEC, STORE>(c, k, s, e, ch); }
 		}
-#if !RXB_CHUNK_BRANCH
-		{
-			const bool cs = (u == 0u);
-#pragma unroll
-			for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
-#pragma unroll
-				for (int j = 5; j > 0; j--) { s.h[l][j] = cs ? s.h[l][j - 1] : s.h[l][j]; }
-			}
-		}
+#else
+		if (u == 0u) { front_chunk_start<P, SPEC, STORE>(c, k, s, e, ch); }
 #endif
-		front_block<P, SPEC, STORE>(c, k, s, e, v, u);
-		u += 8u;
-		// keep the consumer of the prefetched block BEHIND this block's work: without the (empty) asm the
-		// compiler copies vn right after issuing the load and every warp then waits out the full DRAM latency
-		asm volatile("" : "+r"(vn[0]), "+r"(vn[1]), "+r"(vn[2]), "+r"(vn[3]), "+r"(vn[4]), "+r"(vn[5]), "+r"(vn[6]), "+r"(vn[7])
-		             : "r"(e.rel), "r"(s.pre_i));
+		if constexpr (INPLACE) {
+			// scale first; the block's registers are free from here on, so the next block is loaded
+			// straight into them and has the whole rest of this block's work to arrive
+			uint32_t x[8];
+			const bool rot = Spec<SPEC>::rotate(c);
 #pragma unroll
-		for (int j = 0; j < 8; j++) { v[j] = vn[j]; }
+			for (int j = 0; j < 8; j++) { x[j] = scale_rot_pack(v[j], j, rot); }
+			ldg256_after(in + 2 * (size_t)tn, v, x[7]);
+			front_block_packed<P, SPEC, STORE>(c, k, s, e, x, u);
+			u += 8u;
+		} else {
+			front_block<P, SPEC, STORE>(c, k, s, e, v, u);
+			u += 8u;
+			// keep the consumer of the prefetched block BEHIND this block's work: without the (empty) asm the
+			// compiler copies vn right after issuing the load and every warp then waits out the full DRAM latency
+			asm volatile("" : "+r"(vn[0]), "+r"(vn[1]), "+r"(vn[2]), "+r"(vn[3]), "+r"(vn[4]), "+r"(vn[5]), "+r"(vn[6]), "+r"(vn[7])
+			             : "r"(e.rel), "r"(s.pre_i));
+#pragma unroll
+			for (int j = 0; j < 8; j++) { v[j] = vn[j]; }
+		}
 	}
 }
 
@@ -769,6 +905,8 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	const long long g = (long long)it.b * k.n_own + (tid - k.n_extra);
 	const long long start = g * k.Sf;
 	if (g < 0 || start >= k.n) { return; }
+	// the squelch/level pre-pass only sums: the warm-up segments belong to the previous item's sums
+	if (SPEC == 2 && k.reduce_mode == 1 && tid < k.n_extra) { return; }
 	const long long end = start + k.Sf < k.n ? start + k.Sf : k.n;
 	long long t0 = start - k.halo;
 	FrontState<P, SPEC> s;
@@ -865,6 +1003,9 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		if (active || q == 0) {
 			int ws = p.ga - k.W_dec;
 			if (ws < 0) { ws = 0; }
+#if RXB_BE_QUADS
+			ws &= ~3;           // a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
+#endif
 			if (it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
 			if (c.deemph) {
 				if (c.a_even) { back_replay<true>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, p.ga, lo, hi); }
@@ -1176,6 +1317,7 @@ static void fm_fill_dev(rxb200_fm *h)
 	d.fast = p.rate_out; d.slow = p.rate_out2; d.lpr_div = d.resample ? (p.rate_out / p.rate_out2) : 1;
 	d.offset_tuning = p.offset_tuning;
 	for (int j = 0; j < 6; j++) { d.fir[j] = k_droop9_host[d.P][j]; }
+	d.fir_bias = (int)((unsigned)FIR_B * (2u * (unsigned)(d.fir[1] + d.fir[2] + d.fir[3] + d.fir[4]) + (unsigned)d.fir[5]));
 	d.atan_lut = h->d_atan_lut;
 }
 
@@ -1446,7 +1588,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	if (blocks > total_work) { blocks = total_work; }
 	int launches = 0;
 	auto run_fused = [&](int reduce_mode) -> int {
-		k.reduce_mode = reduce_mode;
+		k.reduce_mode = reduce_mode; k.one = 1;
 		RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
 		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev0, h->stream)); }
 		h->kern<<<(unsigned)blocks, FM_THREADS, smem, h->stream>>>(dv, k);

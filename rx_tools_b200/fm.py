@@ -41,6 +41,10 @@ class FmParams:
     offset_tuning: int = 0
     report_levels: int = 0
 
+    def reference_fields(self) -> dict:
+        """The fields that exist in the reference's demod_state (everything but library-only switches)."""
+        return {f.name: int(getattr(self, f.name)) for f in fields(self) if f.name != "report_levels"}
+
     def to_c(self) -> _lib.FmParamsC:
         return _lib.FmParamsC(*[int(getattr(self, f.name)) for f in fields(self)])
 

@@ -31,7 +31,7 @@ def _run(cmd, env=None):
 
 
 def _oracle_params(p):
-    return oracle.FmParams(**{k: v for k, v in p.__dict__.items() if k != "report_levels"})
+    return oracle.FmParams(**p.reference_fields())
 
 
 @pytest.mark.parametrize("args,kw", [

@@ -34,7 +34,7 @@ def test_fm_one_gib_prefix_and_split_calls(port):
     full = out1[:n1].cpu().numpy()
     # (a) prefix == oracle on the first 8 chunks
     k = 8 * CHUNK16
-    want = port.fm_run(oracle.FmParams(**p.__dict__), period[:k], CHUNK16)
+    want = port.fm_run(oracle.FmParams(**p.reference_fields()), period[:k], CHUNK16)
     assert np.array_equal(full[:want.size], want)
     # (b) two calls (split on a chunk boundary) == one call
     dem.reset()
