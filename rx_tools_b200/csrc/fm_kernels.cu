@@ -316,6 +316,44 @@ __device__ __noinline__ int disc_std(int cr, int cj)
 	return (int)(angle / 3.14159 * (double)(1 << 14));
 }
 
+// polar_discriminant without libm's general-purpose atan2: the result is only needed to the integer
+// below it, so a 14-term odd polynomial on [0, 1] (|error| < 7e-13 rad, i.e. < 4e-9 output units) plus a
+// division by fp32 reciprocal + one Newton step decides almost every sample; values within 1e-5 of an
+// integer (where the truncation could flip) go through disc_std.  Same result as disc_std otherwise.
+__device__ __forceinline__ int disc_std_lean(int cr, int cj)
+{
+	if (cj == 0 && cr >= 0) { return 0; }                    // atan2(0, x >= 0) == 0 exactly (also x == y == 0)
+	const double y = (double)cj, x = (double)cr;
+	const double ay = fabs(y), ax = fabs(x);
+	const double a = fmin(ax, ay), b = fmax(ax, ay);         // b >= 1 here
+	float rf;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(b)));
+	double r = (double)rf;
+	r = fma(r, fma(-b, r, 1.0), r);                          // relative error ~2^-46
+	const double t = a * r, u = t * t;
+	double p = -0.00023006126561948349;
+	p = fma(p, u, 0.001914706015773981);
+	p = fma(p, u, -0.0074929064903861186);
+	p = fma(p, u, 0.018612363543602756);
+	p = fma(p, u, -0.03374387219298904);
+	p = fma(p, u, 0.04926117444681421);
+	p = fma(p, u, -0.06301031978620865);
+	p = fma(p, u, 0.07589599479154154);
+	p = fma(p, u, -0.09070400517070532);
+	p = fma(p, u, 0.11108328001324017);
+	p = fma(p, u, -0.1428547415701187);
+	p = fma(p, u, 0.1999998816752856);
+	p = fma(p, u, -0.33333333059437525);
+	p = fma(p, u, 0.9999999999811207);
+	double ang = t * p;
+	if (ay > ax) { ang = 1.5707963267948966 - ang; }
+	if (cr < 0) { ang = 3.141592653589793 - ang; }
+	if (cj < 0) { ang = -ang; }
+	const double v = ang * (16384.0 / 3.14159);
+	if (fabs(v - rint(v)) < 1e-5) { return disc_std(cr, cj); }
+	return (int)v;
+}
+
 // fast_atan2 (src/rtl_fm.c:485-506), int32 wrap-around preserved.  The two branches of the reference
 //   x >= 0: pi/4  - pi/4 * (x - |y|) / (x + |y|)        x < 0: 3pi/4 - pi/4 * (x + |y|) / (|y| - x)
 // share the divisor |x| + |y|; the quotient is bounded by 4096 whenever that divisor is positive (also
@@ -481,7 +519,8 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 		int br = s.pre_i, bj = s.pre_q;
 		int cr = add_w(mul_w(di, br), mul_w(dq, bj));       // x[n] * conj(x[n-1]) (src/rtl_fm.c:470-474)
 		int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
-		if (e.first_in_chunk || am == RXB200_ATAN_STD) { pcm = disc_std(cr, cj); }   // F8
+		if (am == RXB200_ATAN_STD) { pcm = disc_std_lean(cr, cj); }
+		else if (e.first_in_chunk) { pcm = disc_std(cr, cj); }                     // F8: one sample per chunk, out of line
 		else if (am == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
 		else if (am == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }
 		else { pcm = disc_ale(di, dq, br, bj); }

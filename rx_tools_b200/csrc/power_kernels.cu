@@ -31,6 +31,7 @@ struct PowArgs {
 	int ds, ds_passes, boxcar, fir_on;   // small-span decimators (src/rtl_power.c:721-743)
 	int fir[6];                          // cic_9_tables[ds_passes][0..5]
 	int tables_in_smem;                  // 0: sine/window stay in global memory (very large N)
+	int triv;                            // Sinewave[0] == 0 and Sinewave[N/2] in {0, 1}: W^0 and W^(N/4) have a zero component
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -365,6 +366,23 @@ __device__ __forceinline__ void bfly(Cx &lo, Cx &hi, int wr, int wi)
 	lo.im = qi + ti;
 }
 
+// The same butterfly when the twiddle has a zero component: FIX_MPY(0, v) = (0 + 2^14) >> 15 = 0 exactly,
+// so W^0 (wi == 0) and W^(N/4) (wr == 0) need two products instead of four.
+__device__ __forceinline__ void bfly_w0(Cx &lo, Cx &hi, int wr)
+{
+	const int vr = (int)(int16_t)hi.re, vi = (int)(int16_t)hi.im;
+	const int tr = q15(wr, vr), ti = q15(wr, vi);
+	const int qr = (int)((unsigned)lo.re << 16) >> 17, qi = (int)((unsigned)lo.im << 16) >> 17;
+	hi.re = qr - tr; hi.im = qi - ti; lo.re = qr + tr; lo.im = qi + ti;
+}
+__device__ __forceinline__ void bfly_wq(Cx &lo, Cx &hi, int wi)
+{
+	const int vr = (int)(int16_t)hi.re, vi = (int)(int16_t)hi.im;
+	const int tr = -q15(wi, vi), ti = q15(wi, vr);
+	const int qr = (int)((unsigned)lo.re << 16) >> 17, qi = (int)((unsigned)lo.im << 16) >> 17;
+	hi.re = qr - tr; hi.im = qi - ti; lo.re = qr + tr; lo.im = qi + ti;
+}
+
 __device__ __forceinline__ void tw_unpack(uint32_t w, int &wr, int &wi) { wr = plo(w); wi = phi(w); }
 
 // three (or, on the last trip, the last `nst`) stages on the eight points x[j], j = (j2 j1 j0)
@@ -394,6 +412,27 @@ __device__ __forceinline__ void trip_stages(Cx (&x)[8], const uint32_t *tw, int 
 			bfly(x[2 * jj], x[2 * jj + 1], wr, wi);
 		}
 	}
+}
+
+// stages 0..2 (the first trip): the twiddle index depends only on the point's position j among the
+// thread's eight, and ten of the twelve butterflies use W^0 or W^(N/4)
+template <int E>
+__device__ __forceinline__ void trip_first_triv(Cx (&x)[8], const uint32_t *tw)
+{
+	constexpr int N = 1 << E;
+	int w0r, w0i, wqr, wqi, wr, wi;
+	tw_unpack(tw[0], w0r, w0i);
+	tw_unpack(tw[N / 4], wqr, wqi);
+#pragma unroll
+	for (int j = 0; j < 4; j++) { bfly_w0(x[j], x[j + 4], w0r); }
+	bfly_w0(x[0], x[2], w0r); bfly_w0(x[1], x[3], w0r);
+	bfly_wq(x[4], x[6], wqi); bfly_wq(x[5], x[7], wqi);
+	bfly_w0(x[0], x[1], w0r);
+	bfly_wq(x[2], x[3], wqi);
+	tw_unpack(tw[N / 8], wr, wi);
+	bfly(x[4], x[5], wr, wi);
+	tw_unpack(tw[N / 8 + N / 4], wr, wi);
+	bfly(x[6], x[7], wr, wi);
 }
 
 template <int E>
@@ -492,7 +531,8 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 				}
 			}
 			const int rA = s0 > 0 ? (int)(__brev((unsigned)A) >> (32 - (s0 > 0 ? s0 : 1))) : 0;
-			trip_stages<E>(x, tw, rA, s0, first);
+			if (t == 0 && first == 0 && a.triv) { trip_first_triv<E>(x, tw); }
+			else { trip_stages<E>(x, tw, rA, s0, first); }
 			if (!last) {
 				// store in the layout of the next trip: slot n -> n + (n >> (lbw' + 3)) << lbw'
 				const int s0n = (t + 1 == NT - 1 && REM != 0) ? (E - 3) : 3 * (t + 1);
@@ -509,8 +549,8 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 		// real_conj accumulate (:664-668, :760-768): this thread's slots are n = 8*uu + j
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
-			const int ur = (int)((unsigned)x[j].re << 16), ui = (int)((unsigned)x[j].im << 16);   // (v << 16)^2 >> 32 == v*v
-			long long pw = (long long)__mulhi(ur, ur) + (long long)__mulhi(ui, ui);
+			const int vr = (int)(int16_t)x[j].re, vi = (int)(int16_t)x[j].im;      // the reference's int16 store
+			const long long pw = (long long)((unsigned)(vr * vr) + (unsigned)(vi * vi));   // <= 2^31: fits 32 bits unsigned
 			if (a.peak_hold) { acc[j] = pw > acc[j] ? pw : acc[j]; } else { acc[j] += pw; }
 		}
 	}
@@ -591,6 +631,7 @@ struct rxb200_power {
 	int n_sm;
 	cudaEvent_t ev0, ev1;
 	void *d_db = nullptr; size_t db_cap = 0;   // csv_dbm staging (rxb200_power_read_db)
+	int triv = 0;                              // see PowArgs::triv
 };
 
 static int power_validate(const rxb200_power_params *p)
@@ -643,6 +684,7 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 		else { rxb200_sine_table(params->bin_e, sine.data()); }
 		// (int16)(x * w) depends only on w modulo 2^16, so the table is kept as int16
 		for (size_t i = 0; i < N; i++) { win[i] = (int16_t)window_coefs[i]; }
+		h->triv = (N >= 8 && sine[0] == 0 && (sine[N / 2] == 0 || sine[N / 2] == 1)) ? 1 : 0;
 		RXB_CUDA(cudaMalloc(&h->d_sine, sine.size() * sizeof(int16_t)));
 		RXB_CUDA(cudaMalloc(&h->d_window, win.size() * sizeof(int16_t)));
 		RXB_CUDA(cudaMemcpy(h->d_sine, sine.data(), sine.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
@@ -719,7 +761,7 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 	PowArgs a;
 	a.bufs = d_hop_bufs; a.avg = h->d_avg; a.sine = h->d_sine; a.window = h->d_window;
 	a.n_pass = n_pass; a.n_hops_call = nh; a.hop_begin = hop_begin; a.buf_len = h->p.buf_len;
-	a.bin_e = h->p.bin_e; a.peak_hold = h->p.peak_hold;
+	a.bin_e = h->p.bin_e; a.peak_hold = h->p.peak_hold; a.triv = h->triv;
 	a.ds = h->p.downsample; a.ds_passes = h->p.downsample_passes; a.boxcar = h->p.boxcar;
 	a.fir_on = (h->p.comp_fir_size == 9 && h->p.downsample_passes >= 1 && h->p.downsample_passes <= 10) ? 1 : 0;
 	for (int j = 0; j < 6; j++) { a.fir[j] = k_cic9_power[h->p.downsample_passes <= 10 ? h->p.downsample_passes : 0][j]; }
