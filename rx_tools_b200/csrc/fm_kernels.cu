@@ -745,6 +745,26 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 	}
 }
 
+// What a piece does to the states of an open bracket [lo, hi]: both ends are run through PCM [m, m_end);
+// returns non-zero when either end moved at any step.
+enum { PK_OPEN = 0, PK_EXACT = 1, PK_MERGED = 2, PK_IDENT = 3 };
+template <bool EVEN>
+__device__ __forceinline__ int back_probe(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
+{
+	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
+	const unsigned magic = c.a_magic;
+	int moved = 0;
+	for (; m < m_end; m++) {
+		const int x = pcm_load(pcm_s, m);
+		int nl, nh;
+		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, x + bias, magic, K); nh = deemph_fast<EVEN>(hi, x, x + bias, magic, K); }
+		else { nl = deemph_step(c, lo, x); nh = deemph_step(c, hi, x); }
+		moved |= (nl ^ lo) | (nh ^ hi);
+		lo = nl; hi = nh;
+	}
+	return moved;
+}
+
 // Outputs [oa, ob) of one lane from an exact state: per output, de-emphasise the group's samples,
 // sum them and divide by the integer rate ratio (deemph_filter :673-680, low_pass_real :396-407).
 // `phase` is the resampler phase at the first group's start; right after an emission it is < slow, so a
@@ -1016,7 +1036,7 @@ __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.
 
 template <int SPEC>
 __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
-                                          const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok)
+                                          const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok, int *s_start)
 {
 	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
 	int16_t *__restrict__ out = k.out + (size_t)it.ch * (size_t)k.out_stride;
@@ -1034,11 +1054,12 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	axs.chunk = k.chunk; axs.box_n0 = it.box_n0; axs.n_chunks = k.n_chunks; axs.m_lo = it.m_lo;
 	axs.cur = -1; axs.sub = 0; axs.acc = 0;
 	AdcCtx *ax = (SPEC == 2 && c.adc_on && (axs.adc || axs.sums)) ? &axs : nullptr;
+	// ---- pass 1: every lane brackets the state at its piece start; a closed bracket is an exact start
+	const Piece p = make_piece(c, it, carry, o_first, o_end, per, q);
+	const bool active = p.oa < p.ob;
+	int kind = PK_EXACT;
 	{
-		const Piece p = make_piece(c, it, carry, o_first, o_end, per, q);
-		const bool active = p.oa < p.ob;
 		int lo = -32768, hi = 32767, avg = 0, m_run = p.ga;
-		bool start_ok = true;
 		if (active || q == 0) {
 			int ws = p.ga - k.W_dec;
 			if (ws < 0) { ws = 0; }
@@ -1049,40 +1070,90 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 			if (c.deemph) {
 				if (c.a_even) { back_replay<true>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, p.ga, lo, hi); }
 			}
-			start_ok = !c.deemph || (lo == hi);
 			avg = lo;
+			if (c.deemph && lo != hi) {
+				// Open bracket (quiet input: the rounding IIR has a dead zone).  Summarise what the piece does to
+				// ANY state in [lo, hi] by running both ends through it: if they meet, the end state is exact
+				// whatever the start was; if neither ever moves, no state in between moves either (the fixed
+				// points of one step form an interval), so the piece passes its start state through.
+				const int ge = active ? (int)(group_start(c, p.ob, it.phase0) - it.m_lo) : p.ga;
+				const int moved = c.a_even ? back_probe<true>(c, pcm_s, p.ga, ge, lo, hi) : back_probe<false>(c, pcm_s, p.ga, ge, lo, hi);
+				kind = (lo == hi) ? PK_MERGED : (moved == 0 ? PK_IDENT : PK_OPEN);
+				avg = lo; m_run = ge;
+			}
 		}
-		if (active && start_ok) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
-		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = start_ok ? 1 : 0;
+		if (active && kind == PK_EXACT) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
+		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = (unsigned char)kind;
 	}
 	bar_sync(BAR_BE, lanes);
-	if (q != 0) { return; }
-	// Pieces whose bracket was still open take their left neighbour's exact end state, left to right
-	// (piece 0: the previous item of this channel, an older ticket, through its published word).
-	for (int j = 0; j <= last_q; j++) {
-		if (s_ok[j]) { continue; }
-		int avg;
-		if (j == 0) {
-			volatile int *pp = k.pub + 4 * (size_t)(work - 1);
-			while (pp[0] == 0) { __nanosleep(64); }
-			__threadfence();
-			avg = pp[1];
-		} else { avg = s_avg[j - 1]; }
-		const Piece p = make_piece(c, it, carry, o_first, o_end, per, j);
-		int m_run = p.ga;
-		if (p.oa < p.ob) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
-		s_avg[j] = avg; s_mrun[j] = m_run; s_ok[j] = 1;
-		atomicAdd(k.fix_count, 1);
+	// ---- chain (thread 0).  Across items the published word is a decoupled look-back: 1 = exact end state,
+	// 2 = "this item passes its start state through" (the reader keeps walking back).  An item whose end state
+	// is anchored by one of its own pieces publishes before it looks at anybody else.
+	if (q == 0) {
+		volatile int *pub = k.pub;
+		auto serial_end = [&](int j, int start) -> int {          // PK_OPEN: the piece's de-emphasis from a known start
+			const Piece pj = make_piece(c, it, carry, o_first, o_end, per, j);
+			int l2 = start, h2 = start;
+			if (pj.oa < pj.ob) {
+				const int ge = (int)(group_start(c, pj.ob, it.phase0) - it.m_lo);
+				if (c.a_even) { back_probe<true>(c, pcm_s, pj.ga, ge, l2, h2); } else { back_probe<false>(c, pcm_s, pj.ga, ge, l2, h2); }
+			}
+			return l2;
+		};
+		auto publish = [&](int flag, int value) {
+			volatile int *mp = pub + 4 * (size_t)work;
+			if (flag == 1) { mp[1] = value; __threadfence(); }
+			mp[0] = flag;
+		};
+		int anchor = -1, n_open = 0, published = 0, fixes = 0;
+		for (int j = last_q; j >= 0; j--) {
+			const int kj = s_ok[j];
+			if (kj == PK_EXACT || kj == PK_MERGED) { anchor = j; break; }
+			if (kj == PK_OPEN) { n_open++; }
+		}
+		if (!last_cta) {
+			if (anchor >= 0) {
+				int cur = s_avg[anchor];
+				for (int j = anchor + 1; j <= last_q; j++) { if (s_ok[j] == PK_OPEN) { cur = serial_end(j, cur); } }
+				publish(1, cur); published = 1;
+			} else if (n_open == 0) { publish(2, 0); published = 2; }
+		}
+		// start states, left to right (piece 0: the closest older item of this channel that knows its end state)
+		int cur = 0;
+		for (int j = 0; j <= last_q; j++) {
+			const int kj = s_ok[j];
+			if (kj == PK_EXACT) { cur = s_avg[j]; continue; }
+			int start;
+			if (j == 0) {
+				int w = work - 1;
+				for (;;) {
+					const int f = pub[4 * (size_t)w];
+					if (f == 0) { __nanosleep(32); continue; }
+					if (f == 1) { __threadfence(); start = pub[4 * (size_t)w + 1]; break; }
+					w--;                                              // f == 2: that item passes its start through
+				}
+			} else { start = cur; }
+			s_start[j] = start;
+			if (kj == PK_MERGED) { cur = s_avg[j]; }
+			else if (kj == PK_IDENT) { cur = start; }
+			else { cur = serial_end(j, start); }
+			s_avg[j] = cur;
+			fixes++;
+		}
+		if (!last_cta && published != 1) { publish(1, s_avg[last_q]); }
+		if (fixes) { atomicAdd(k.fix_count, fixes); }
 	}
+	bar_sync(BAR_BE, lanes);
+	// ---- pass 2: the pieces that had no exact start in pass 1 now run from the state the chain gave them
+	if (active && kind != PK_EXACT) {
+		int avg = s_start[q], m_run = p.ga;
+		run_piece(c, pcm_s, out, p, m_run, avg, ax, store);
+	}
+	if (q != 0) { return; }
 	// end state of the item = state after its last piece
 	int fin_avg = s_avg[last_q];
 	const int fin_m = s_mrun[last_q];
-	if (!last_cta) {
-		volatile int *mp = k.pub + 4 * (size_t)work;
-		mp[1] = fin_avg;
-		__threadfence();
-		mp[0] = 1;
-	} else {
+	if (last_cta) {
 		// tail of the stream: samples after the last emitted output stay in the accumulator
 		int acc = (it.m_lo == 0 && fin_m == 0) ? (int)carry[ST_LPR_ACC] : 0;
 		for (int m = fin_m; m < it.m_hi; m++) {
@@ -1111,6 +1182,7 @@ __global__ void __launch_bounds__(FM_THREADS, (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P
 	__shared__ int s_work;
 	__shared__ int s_avg[FM_BE_MAX_LANES], s_mrun[FM_BE_MAX_LANES];
 	__shared__ unsigned char s_ok[FM_BE_MAX_LANES];
+	__shared__ int s_start[FM_BE_MAX_LANES];
 	const int tid = threadIdx.x;
 	const int total_work = k.n_ch * k.n_cta;
 	const bool direct = Spec<SPEC>::direct(k);
@@ -1131,7 +1203,7 @@ __global__ void __launch_bounds__(FM_THREADS, (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P
 			continue;
 		}
 		__syncthreads();
-		if (tid < k.be_lanes) { back_item<SPEC>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok); }
+		if (tid < k.be_lanes) { back_item<SPEC>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok, s_start); }
 	}
 }
 

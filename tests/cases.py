@@ -92,6 +92,13 @@ def fm_cases(scale: int = 1) -> list[FmCase]:
                                                     custom_atan=ATAN_FAST, deemph=1, deemph_a=23,
                                                     rate_out=300_000, rate_out2=48_000),
                      lambda: np.concatenate([_wb(n // 4, seed=11)(), np.zeros(2 * (n - n // 4), dtype=np.int16)]), C))
+    # a murmur: PCM wanders by a few tens of LSB, so brackets stay open and only sometimes move or meet
+    # (exercises every piece kind of the back end's chain: exact / merged / pass-through / open)
+    cs.append(FmCase("murmur_deemph", FmParams(downsample=8, downsample_passes=3, comp_fir_size=9,
+                                               custom_atan=ATAN_FAST, deemph=1, deemph_a=23, rate_out=300_000,
+                                               rate_out2=48_000),
+                     lambda: synth.fm_iq(n, fs=2.4e6, deviation_hz=260.0, tones=[(31.0, 1.0), (5.0, 0.6)],
+                                         amplitude=14000, noise_lsb=0, seed=17), C))
     # ragged: stream not a multiple of the chunk; short last chunk
     cs.append(FmCase("ragged_tail", FmParams(downsample=8, downsample_passes=3, comp_fir_size=9,
                                              custom_atan=ATAN_FAST, deemph=1, deemph_a=23, rate_out=300_000,

@@ -45,7 +45,7 @@ def test_fm_matches_oracle_and_golden(case, port):
 
 @pytest.mark.parametrize("seg", [64, 256, 4096])
 @pytest.mark.parametrize("name", ["cfg2B", "cfg2A", "nbfm_D42_lut", "wbfm_default", "F9_P5_lut", "raw_D4", "zeros_deemph",
-                                  "burst_then_silence", "fullscale_noise_P3"])
+                                  "burst_then_silence", "fullscale_noise_P3", "murmur_deemph"])
 def test_fm_small_segments(name, seg, port):
     """Tiny segments: every thread boundary falls inside chunks, replay regions overlap chunk starts, and the
     de-emphasis bracket rarely closes -> exercises the serial fix-up."""
