@@ -10,15 +10,16 @@
 //     thread runs scale/rotate/decimate/FIR/discriminator over its own Sf-sample segment, all state
 //     in registers, after replaying `halo` samples so the finite-memory filters are exact; the
 //     demodulated PCM (one int16 per decimated sample) goes to shared memory only.
-//   * BACK END: warp 0 runs the serial stages (deemph_filter, low_pass_real) over the CTA's PCM,
-//     one contiguous piece per lane.  deemph_filter is a rounding (non-linear) IIR, so each lane
-//     replays W_dec PCM samples before its piece from BOTH extreme states (-32768 / +32767): the
-//     step map is monotone in the state, the true state is bracketed, and once the two
-//     trajectories meet it is exact (SURVEY.md §7 hard part 2).  Lanes whose bracket has not
-//     closed (quiet input: the IIR has a dead zone) are re-run from their left neighbour's exact
-//     end state, in-warp via shuffles and across CTAs via a published end state (CTAs take work
-//     tickets in order, so a CTA only ever waits for an older one).  The result is bit-exact for
-//     every input.
+//   * BACK END: the first `be_lanes` threads run the serial stages (deemph_filter, low_pass_real)
+//     over the item's PCM, one contiguous piece of OUTPUTS per lane.  deemph_filter is a rounding
+//     (non-linear) IIR, so each lane replays W_dec PCM samples before its piece from BOTH extreme
+//     states (-32768 / +32767): the step map is monotone in the state, the true state is
+//     bracketed, and once the two trajectories meet it is exact (SURVEY.md §7 hard part 2).  A
+//     bracket that stays open (quiet input: the IIR has a dead zone) is summarised per piece --
+//     merged / pass-through / open -- and resolved by thread 0 plus a decoupled look-back over the
+//     items' published words (items are ticketed in order, so a reader only waits for older
+//     ones); those pieces then produce their outputs in a second parallel pass.  The result is
+//     bit-exact for every input.
 //   * The halo/warm-up PCM a CTA needs from before its stretch is recomputed by `n_extra` of its
 //     own threads, so nothing but the CS16 stream is read from HBM and nothing but PCM written.
 // Per-chunk semantics (rotation phase restart, fifth_order dropping the last sample of a chunk,
@@ -34,9 +35,6 @@
 namespace rxb {
 
 #define FM_THREADS 256
-#ifndef RXB_CHUNK_BRANCH
-#define RXB_CHUNK_BRANCH 1
-#endif
 #ifndef RXB_L2_CLAMP
 #define RXB_L2_CLAMP 0
 #endif
@@ -52,8 +50,8 @@ namespace rxb {
 #ifndef RXB_RCP_APPROX
 #define RXB_RCP_APPROX 1     // fast_atan2: bare MUFU.RCP (the +-1 remainder correction absorbs its 1 ulp)
 #endif
-#ifndef RXB_CHUNK_VOTE
-#define RXB_CHUNK_VOTE 1     // chunk-start bookkeeping behind a warp vote instead of 16 predicated moves per block
+#ifndef RXB_CHUNK_LOOP
+#define RXB_CHUNK_LOOP 1     // chunk-start bookkeeping in a one-trip loop ptxas cannot if-convert (else: 16 predicated moves per block)
 #endif
 #ifndef RXB_FIR_PACKED
 #define RXB_FIR_PACKED 1     // droop FIR on biased packed history: symmetric taps added two lanes at a time
@@ -896,7 +894,7 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 		}
 #endif
 		if (u >= (unsigned)k.chunk) { u = 0u; }
-#if RXB_CHUNK_VOTE
+#if RXB_CHUNK_LOOP
 		// a lane meets a chunk start once in chunk/8 blocks.  Left alone, ptxas if-converts the bookkeeping into
 		// ~16 predicated-off moves in EVERY block; a loop (trip count k.one == 1, unknown to the compiler) cannot
 		// be predicated, so the common path pays one branch
@@ -1654,11 +1652,9 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		double best_cost = 1e30;
 		for (long long sf = Sf; sf >= G && sf * 10 >= Sf * 6; sf -= G) {
 			if (!geometry(sf)) { continue; }
-			int occ = per_sm;
 			double waves = (double)(n_cta * h->n_channels) / slots;
 			double cost = (waves <= 1.0 ? 1.0 : ceil(waves) / waves) * (1.0 + (double)halo / (double)sf) *
 			              ((double)FM_THREADS / (double)n_own);
-			(void)occ;
 			if (cost < best_cost - 1e-9) { best_cost = cost; best = sf; }
 		}
 		Sf = best;
