@@ -34,7 +34,10 @@
 
 namespace rxb {
 
-#define FM_THREADS 256
+#ifndef FM_THREADS
+#define FM_THREADS 256       // threads (= front-end segments) per CTA; 128 puts one warp of a CTA on each SM sub-partition
+#endif
+#define FM_OCC_SCALE (256 / FM_THREADS)
 #ifndef RXB_L2_CLAMP
 #define RXB_L2_CLAMP 0
 #endif
@@ -71,6 +74,16 @@ namespace rxb {
 #ifndef RXB_ATAN_V
 #define RXB_ATAN_V 1
 #endif
+#ifndef RXB_FIR_TRANSPOSED
+#define RXB_FIR_TRANSPOSED 0 // droop FIR in transposed form: 9 int32 partial sums per component instead of a sample history
+#endif
+#ifndef RXB_PCM_SADDR
+#define RXB_PCM_SADDR 0      // front-end PCM stores through a 32-bit shared-window address computed once per item
+#endif
+#ifndef RXB_DEEMPH_V
+#define RXB_DEEMPH_V 0       // 1: odd deemph_a: avg += mulhi(2 (x - avg) + a, floor(2^32 / 2a)), two dependent FMA-pipe instructions per step
+#endif
+#define FM_FIR_WORDS (RXB_FIR_TRANSPOSED ? 18 : 9)
 #define FM_MAX_PACKED 3          // fifth_order passes run as packed I/Q SWAR (bias keeps lanes unsigned)
 
 // ------------------------------------------------------------------------------ device config
@@ -122,7 +135,7 @@ enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC,
        ST_SQ_HITS, ST_ADC, ST_RDC_I, ST_RDC_Q, ST_HDR = 16 };
 
 static inline int fm_packed_levels(int P, int wide) { return wide ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED); }
-static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
+static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + FM_FIR_WORDS; }
 
 constexpr uint32_t L0_BIAS = RXB_L0_UNBIASED ? 0x00800080u : 0u;   // pass-0 lanes are unbiased in registers; carry words keep the biased format
 constexpr unsigned FIR_B = 16384u;
@@ -149,7 +162,11 @@ struct FrontState {
 	uint32_t h[PL > 0 ? PL : 1][6];
 	// scalar passes (level >= 3): the reference's window a..f plus the odd sample waiting for its pair
 	int wi[PS > 0 ? PS : 1][6], wq[PS > 0 ? PS : 1][6], pi[PS > 0 ? PS : 1], pq[PS > 0 ? PS : 1];
+#if RXB_FIR_TRANSPOSED
+	int fa[2][9];              // generic_fir as partial sums of the next nine outputs (I, Q), see droop9_transposed
+#else
 	uint32_t fh[9];            // generic_fir history, I low / Q high half-word (raw int16)
+#endif
 	int pre_i, pre_q;
 };
 
@@ -168,8 +185,13 @@ __device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 		for (int j = 0; j < 6; j++) { s.wi[l][j] = 0; s.wq[l][j] = 0; }
 		s.pi[l] = 0; s.pq[l] = 0;
 	}
+#if RXB_FIR_TRANSPOSED
+#pragma unroll
+	for (int j = 0; j < 9; j++) { s.fa[0][j] = 0; s.fa[1][j] = 0; }
+#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(0u) : 0u; }
+#endif
 	s.pre_i = s.pre_q = 0;
 }
 
@@ -190,8 +212,13 @@ __device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_
 		for (int j = 0; j < 6; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * l + j]; s.wi[l][j] = lo16(w); s.wq[l][j] = hi16(w); }
 		uint32_t w = g[ST_HDR + 6 * PL + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
 	}
+#if RXB_FIR_TRANSPOSED
+#pragma unroll
+	for (int j = 0; j < 9; j++) { s.fa[0][j] = (int)g[ST_HDR + 6 * PL + 7 * PS + j]; s.fa[1][j] = (int)g[ST_HDR + 6 * PL + 7 * PS + 9 + j]; }
+#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * PS + j]; s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(w) : w; }
+#endif
 }
 
 template <int P, int SPEC>
@@ -211,8 +238,13 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * PL + 7 * l + j] = pack2(s.wi[l][j], s.wq[l][j]); }
 		g[ST_HDR + 6 * PL + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
 	}
+#if RXB_FIR_TRANSPOSED
+#pragma unroll
+	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = (uint32_t)s.fa[0][j]; g[ST_HDR + 6 * PL + 7 * PS + 9 + j] = (uint32_t)s.fa[1][j]; }
+#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = FrontState<P, SPEC>::FIRB ? fir_unbias_lanes(s.fh[j]) : s.fh[j]; }
+#endif
 }
 
 // ------------------------------------------------------------------------------ stages
@@ -307,6 +339,26 @@ __device__ __forceinline__ void droop9_packed(uint32_t (&h)[9], const int (&c)[6
 	dq = wrap16(aq >> 15);
 }
 
+// Same filter in transposed form.  The reference's sum  y[n] = sum_j g[j] x[n-9+j],  g = (c1 c2 c3 c4 c5 c4 c3 c2 c1),
+// is evaluated in wrapping int32, so any order of the additions gives the same 32 bits.  A[m] holds what the
+// samples seen so far contribute to y[n+m]:  y[n] = A[0];  then x[n] joins every later output,
+//   A[m] <- A[m+1] + g[8-m] x[n]  (m < 8),   A[8] <- g[0] x[n].
+// One IMAD per tap and component writes each partial sum into the register of its successor: no history to
+// shift, nothing to unpack, and the work sits on the FMA pipe instead of the ALU pipe.
+__device__ __forceinline__ void droop9_transposed(int (&a)[2][9], const int (&c)[6], int &di, int &dq)
+{
+	const int yi = wrap16(a[0][0] >> 15), yq = wrap16(a[1][0] >> 15);
+	const int g[9] = {c[1], c[2], c[3], c[4], c[5], c[4], c[3], c[2], c[1]};
+#pragma unroll
+	for (int m = 0; m < 8; m++) {
+		a[0][m] = add_w(a[0][m + 1], mul_w(g[8 - m], di));
+		a[1][m] = add_w(a[1][m + 1], mul_w(g[8 - m], dq));
+	}
+	a[0][8] = mul_w(g[0], di);
+	a[1][8] = mul_w(g[0], dq);
+	di = yi; dq = yq;
+}
+
 // polar_discriminant (src/rtl_fm.c:476-483); note 3.14159.
 __device__ __noinline__ int disc_std(int cr, int cj)
 {
@@ -368,7 +420,7 @@ __device__ __forceinline__ float rcp_est(float x)
 	return __frcp_rn(x);
 #endif
 }
-__device__ __forceinline__ int fast_atan2_i(int y, int x)
+__device__ __forceinline__ int fast_atan2_generic(int y, int x)
 {
 #if RXB_ATAN_V == 0
 	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
@@ -397,6 +449,36 @@ __device__ __forceinline__ int fast_atan2_i(int y, int x)
 	}
 	const int ang = sub_w(xneg ? q3 : q1, q);
 	return y < 0 ? neg_w(ang) : ang;
+#endif
+}
+
+// Common case first: with den = |x| + |y| in [1, 2^19) nothing wraps, d := |x| - |y| has |d| <= den, and both
+// branches of the reference reduce to one non-negative quotient Qa = floor(4096 |d| / den):
+//   x >= 0: pi/4 - sgn(d) Qa        x < 0: 3pi/4 + sgn(d) Qa        (C's '/' truncates, so the sign factors out)
+// The fp32 estimate of a quotient <= 4096 is off by < 2^-10, so its truncation is Qa or a neighbour and one
+// remainder decides.  Everything else (int32 wrap-around, x == y == 0) takes the generic path.
+__device__ __forceinline__ int fast_atan2_lean(int y, int x)
+{
+	const int ax = x < 0 ? neg_w(x) : x, ay = y < 0 ? neg_w(y) : y;
+	const int den = add_w(ax, ay);
+	if ((unsigned)sub_w(den, 1) >= (1u << 19) - 1u) { return fast_atan2_generic(y, x); }
+	const int d = ax - ay;
+	const int n = (d < 0 ? -d : d) << 12;                          // <= 2^31 - 4096
+	int q = __float2int_rz(__int2float_rn(n) * rcp_est(__int2float_rn(den)));
+	const int r = sub_w(n, mul_w(q, den));                         // in (-den, 2 den); the product alone may wrap
+	q += (r >> 31) + (r >= den ? 1 : 0);
+	const int m = ~((x ^ d) >> 31);                                // -1: Qa is subtracted (x and d of one sign), 0: added
+	const int ang = (1 << 12) + ((x >> 31) & (1 << 13)) + ((q ^ m) - m);
+	const int sy = y >> 31;
+	return (ang ^ sy) - sy;
+}
+
+__device__ __forceinline__ int fast_atan2_i(int y, int x)
+{
+#if RXB_ATAN_V == 2
+	return fast_atan2_lean(y, x);
+#else
+	return fast_atan2_generic(y, x);
 #endif
 }
 
@@ -431,6 +513,9 @@ __device__ __forceinline__ int deemph_step(const FmDev &c, int avg, int x)
 {
 	int d = x - avg;
 	if (c.a_use_magic) {
+#if RXB_DEEMPH_V
+		if (!c.a_even) { return avg + __mulhi(2 * d + c.a, (int)c.a_magic); }   // see deemph_fast
+#endif
 		int n = d + c.a_half + c.a_K * c.a;
 		if (c.a_even) { n -= (d <= 0) ? 1 : 0; }
 		return avg + (int)__umulhi((unsigned)n, c.a_magic) - c.a_K;
@@ -483,6 +568,7 @@ struct Spec {
 
 struct EmitCtx {
 	int16_t *pcm;            // shared PCM buffer
+	uint32_t pcm_sa;         // the same as a shared-window byte address
 	int16_t *out;            // channel output (direct_out only)
 	long long m_lo;          // decimated index of pcm[0]
 	int rel;                 // decimated index of the next sample, relative to m_lo
@@ -500,7 +586,11 @@ template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int di, int dq)
 {
 	if (c.fir_on) {
+#if RXB_FIR_TRANSPOSED
+		droop9_transposed(s.fa, c.fir, di, dq);
+#else
 		if constexpr (FrontState<P, SPEC>::FIRB) { droop9_packed(s.fh, c.fir, c.fir_bias, di, dq); } else { droop9(s.fh, c.fir, di, dq); }
+#endif
 	}
 	if (SPEC == 2) {
 		if (k.reduce_mode == 1) {       // rms() inputs of this chunk (src/rtl_fm.c:746-751)
@@ -544,7 +634,14 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 	}
 	if (STORE) {      // the int16 store is the reference's (int16_t) cast
 		if (Spec<SPEC>::direct(k)) { if (SPEC != 2 || k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
-		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
+		else {
+#if RXB_PCM_SADDR
+			// generic-pointer stores make ptxas rebuild the window base (S2UR/UMOV/ULEA) in every block
+			asm volatile("st.shared.u16 [%0], %1;" ::"r"(e.pcm_sa + 2u * (uint32_t)pcm_phys(e.rel)), "h"((short)pcm) : "memory");
+#else
+			e.pcm[pcm_phys(e.rel)] = (int16_t)pcm;
+#endif
+		}
 	}
 	e.rel++;
 }
@@ -683,9 +780,25 @@ __device__ __forceinline__ long long group_start(const FmDev &c, long long o, in
 
 // deemph_filter step on the magic-reciprocal path with the loop-invariant part folded into xb:
 //   xb = x + a/2 + K*a;   avg' = avg + umulhi(xb - avg - [a even && x <= avg], magic) - K
+// Odd a (RXB_DEEMPH_V): c = h always and floor(n / a) == floor((2n + 1) / 2a), where the half-step keeps the
+// argument away from the integers by 1/2a -- more than the error of a truncated reciprocal -- so ONE signed
+// multiply-high is the floor for either sign of n, without bias or correction (host-verified over the range):
+//   xb = 2 x + a;   avg' = avg + mulhi(xb - 2 avg, floor(2^32 / 2a))
+// i.e. an IMAD and an IMAD.HI with avg as the addend: two dependent instructions per step instead of three.
+template <bool EVEN>
+__device__ __forceinline__ int deemph_pre(int x, int bias, int a)
+{
+#if RXB_DEEMPH_V
+	if (!EVEN) { return 2 * x + a; }
+#endif
+	return x + bias;
+}
 template <bool EVEN>
 __device__ __forceinline__ int deemph_fast(int avg, int x, int xb, unsigned magic, int K)
 {
+#if RXB_DEEMPH_V
+	if (!EVEN) { return avg + __mulhi(xb - 2 * avg, (int)magic); }
+#endif
 	int n = xb - avg;
 	if (EVEN) { n -= (x <= avg) ? 1 : 0; }
 	return avg + (int)__umulhi((unsigned)n, magic) - K;
@@ -706,29 +819,29 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
 		for (; (m & 3) != 0 && m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
-			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
+			hi = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
 		}
 #pragma unroll 2
 		for (; m + 4 <= m_end; m += 4) {
 			const int16_t *q = pcm_s + pcm_phys(m);
 			const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
-			lo = deemph_fast<EVEN>(lo, x0, x0 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x0, x0 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x1, x1 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x1, x1 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x2, x2 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x2, x2 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x3, x3 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x3, x3 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x0, deemph_pre<EVEN>(x0, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x0, deemph_pre<EVEN>(x0, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x1, deemph_pre<EVEN>(x1, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x1, deemph_pre<EVEN>(x1, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x2, deemph_pre<EVEN>(x2, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x2, deemph_pre<EVEN>(x2, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x3, deemph_pre<EVEN>(x3, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x3, deemph_pre<EVEN>(x3, bias, c.a), magic, K);
 		}
 		for (; m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
-			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
+			hi = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
 		}
 #else
 		int x = pcm_load(pcm_s, m);
 #pragma unroll 4
 		for (; m < m_end; m++) {
 			int xn = pcm_load(pcm_s, m + 1 < m_end ? m + 1 : m);
-			int xb = x + bias;
+			int xb = deemph_pre<EVEN>(x, bias, c.a);
 			lo = deemph_fast<EVEN>(lo, x, xb, magic, K);
 			hi = deemph_fast<EVEN>(hi, x, xb, magic, K);
 			x = xn;
@@ -755,7 +868,7 @@ __device__ __forceinline__ int back_probe(const FmDev &c, const int16_t *pcm_s, 
 	for (; m < m_end; m++) {
 		const int x = pcm_load(pcm_s, m);
 		int nl, nh;
-		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, x + bias, magic, K); nh = deemph_fast<EVEN>(hi, x, x + bias, magic, K); }
+		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); nh = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); }
 		else { nl = deemph_step(c, lo, x); nh = deemph_step(c, hi, x); }
 		moved |= (nl ^ lo) | (nh ^ hi);
 		lo = nl; hi = nh;
@@ -820,7 +933,7 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 		}
 		for (int j = 0; j < len; j++) {
 			int xn = pcm_load(pcm_s, m + 1);      // one entry of slack exists past the last sample
-			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, x + bias, magic, K); x = wrap16(avg); }
+			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); x = wrap16(avg); }
 			else if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
 			if (ax) { x = adc_apply(c, *ax, m, x); }
 			acc = add_w(acc, x);
@@ -975,7 +1088,11 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	unsigned u = (unsigned)(t0 % k.chunk);
 	const long long m0 = dec_before(c, t0, it.box_n0);
 	EmitCtx e;
-	e.pcm = pcm_s; e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
+	e.pcm = pcm_s; e.pcm_sa = (uint32_t)__cvta_generic_to_shared(pcm_s);
+#if RXB_PCM_SADDR
+	asm volatile("" : "+r"(e.pcm_sa));   // opaque: otherwise the window base is rematerialised at every store
+#endif
+	e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
 	e.rel = (int)(m0 - it.m_lo);
 	e.first_in_chunk = 0;
 	if (P == 0) { e.first_in_chunk = (dec_raw(c, t0 - u, it.box_n0) == dec_raw(c, t0, it.box_n0)) ? 1 : 0; }
@@ -1174,7 +1291,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 // `be_lanes/32` warps run the back end out of the shared PCM buffer.  Work items are handed out by an
 // atomic ticket, oldest first (the cross-item look-back only ever waits for an older ticket).
 template <int P, int SPEC>
-__global__ void __launch_bounds__(FM_THREADS, (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1)))) fm_fused_kernel(const FmDev c, const FmCall k)
+__global__ void __launch_bounds__(FM_THREADS, FM_OCC_SCALE * (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1)))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
@@ -1290,6 +1407,9 @@ __global__ void fm_adc_recur_kernel(const long long *sums, const int *pcm_len, i
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
 static fm_kernel_fn pick_kernel(int P, int spec)
 {
+#ifdef RXB_QUICK   // development builds: only the wbfm P=3 kernel is instantiated (seconds instead of minutes)
+	return (spec == 1 && P == 3) ? fm_fused_kernel<3, 1> : nullptr;
+#else
 	if (spec == 1) {
 		switch (P) {
 		case 0: return fm_fused_kernel<0, 1>;
@@ -1330,6 +1450,7 @@ static fm_kernel_fn pick_kernel(int P, int spec)
 	case 10: return fm_fused_kernel<10, 0>;
 	default: return nullptr;
 	}
+#endif
 }
 
 }  // namespace rxb
@@ -1421,6 +1542,22 @@ static void fm_fill_dev(rxb200_fm *h)
 			if ((unsigned)(((unsigned long long)n * magic) >> 32) != n / (unsigned)d.a) { ok = false; }
 		}
 		if (ok) { d.a_use_magic = 1; d.a_magic = magic; d.a_K = K; }
+#if RXB_DEEMPH_V
+		if (!d.a_even) {
+			// signed form for odd a: mulhi(2n + 1, floor(2^32 / 2a)) == floor(n / a) for every numerator d + h in range
+			d.a_use_magic = 0;
+			if (d.a >= 3) {
+				const long long m2 = 0x100000000LL / (2LL * d.a);
+				const int lim = 65536 + 32768 + d.a;
+				bool ok2 = true;
+				for (int n = -lim; n <= lim && ok2; n++) {
+					const long long fl = n >= 0 ? n / d.a : -((-(long long)n + d.a - 1) / d.a);
+					if ((((2LL * n + 1) * m2) >> 32) != fl) { ok2 = false; }
+				}
+				if (ok2) { d.a_use_magic = 1; d.a_magic = (unsigned)m2; d.a_K = 0; }
+			}
+		}
+#endif
 	}
 	d.resample = (p.rate_out2 > 0 && p.mode != RXB200_MODE_RAW) ? 1 : 0;
 	d.fast = p.rate_out; d.slow = p.rate_out2; d.lpr_div = d.resample ? (p.rate_out / p.rate_out2) : 1;
