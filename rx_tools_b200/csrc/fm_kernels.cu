@@ -6,7 +6,7 @@
 // per complex sample).
 //
 // Decomposition (DESIGN.md "rx_fm kernel"):
-//   * A CTA (256 threads) owns a contiguous stretch of one channel's stream.  FRONT END: every
+//   * A CTA (128 or 256 threads, see fm_cta_threads) owns a contiguous stretch of one channel's stream.  FRONT END: every
 //     thread runs scale/rotate/decimate/FIR/discriminator over its own Sf-sample segment, all state
 //     in registers, after replaying `halo` samples so the finite-memory filters are exact; the
 //     demodulated PCM (one int16 per decimated sample) goes to shared memory only.
@@ -34,10 +34,7 @@
 
 namespace rxb {
 
-#ifndef FM_THREADS
-#define FM_THREADS 256       // threads (= front-end segments) per CTA; 128 puts one warp of a CTA on each SM sub-partition
-#endif
-#define FM_OCC_SCALE (256 / FM_THREADS)
+#define FM_MAX_THREADS 256       // widest CTA; the width is a kernel template parameter (fm_cta_threads picks it)
 #ifndef RXB_L2_CLAMP
 #define RXB_L2_CLAMP 0
 #endif
@@ -74,16 +71,6 @@ namespace rxb {
 #ifndef RXB_ATAN_V
 #define RXB_ATAN_V 1
 #endif
-#ifndef RXB_FIR_TRANSPOSED
-#define RXB_FIR_TRANSPOSED 0 // droop FIR in transposed form: 9 int32 partial sums per component instead of a sample history
-#endif
-#ifndef RXB_PCM_SADDR
-#define RXB_PCM_SADDR 0      // front-end PCM stores through a 32-bit shared-window address computed once per item
-#endif
-#ifndef RXB_DEEMPH_V
-#define RXB_DEEMPH_V 0       // 1: odd deemph_a: avg += mulhi(2 (x - avg) + a, floor(2^32 / 2a)), two dependent FMA-pipe instructions per step
-#endif
-#define FM_FIR_WORDS (RXB_FIR_TRANSPOSED ? 18 : 9)
 #define FM_MAX_PACKED 3          // fifth_order passes run as packed I/Q SWAR (bias keeps lanes unsigned)
 
 // ------------------------------------------------------------------------------ device config
@@ -135,7 +122,7 @@ enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC,
        ST_SQ_HITS, ST_ADC, ST_RDC_I, ST_RDC_Q, ST_HDR = 16 };
 
 static inline int fm_packed_levels(int P, int wide) { return wide ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED); }
-static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + FM_FIR_WORDS; }
+static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
 
 constexpr uint32_t L0_BIAS = RXB_L0_UNBIASED ? 0x00800080u : 0u;   // pass-0 lanes are unbiased in registers; carry words keep the biased format
 constexpr unsigned FIR_B = 16384u;
@@ -162,11 +149,7 @@ struct FrontState {
 	uint32_t h[PL > 0 ? PL : 1][6];
 	// scalar passes (level >= 3): the reference's window a..f plus the odd sample waiting for its pair
 	int wi[PS > 0 ? PS : 1][6], wq[PS > 0 ? PS : 1][6], pi[PS > 0 ? PS : 1], pq[PS > 0 ? PS : 1];
-#if RXB_FIR_TRANSPOSED
-	int fa[2][9];              // generic_fir as partial sums of the next nine outputs (I, Q), see droop9_transposed
-#else
 	uint32_t fh[9];            // generic_fir history, I low / Q high half-word (raw int16)
-#endif
 	int pre_i, pre_q;
 };
 
@@ -185,13 +168,8 @@ __device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 		for (int j = 0; j < 6; j++) { s.wi[l][j] = 0; s.wq[l][j] = 0; }
 		s.pi[l] = 0; s.pq[l] = 0;
 	}
-#if RXB_FIR_TRANSPOSED
-#pragma unroll
-	for (int j = 0; j < 9; j++) { s.fa[0][j] = 0; s.fa[1][j] = 0; }
-#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(0u) : 0u; }
-#endif
 	s.pre_i = s.pre_q = 0;
 }
 
@@ -212,13 +190,8 @@ __device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_
 		for (int j = 0; j < 6; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * l + j]; s.wi[l][j] = lo16(w); s.wq[l][j] = hi16(w); }
 		uint32_t w = g[ST_HDR + 6 * PL + 7 * l + 6]; s.pi[l] = lo16(w); s.pq[l] = hi16(w);
 	}
-#if RXB_FIR_TRANSPOSED
-#pragma unroll
-	for (int j = 0; j < 9; j++) { s.fa[0][j] = (int)g[ST_HDR + 6 * PL + 7 * PS + j]; s.fa[1][j] = (int)g[ST_HDR + 6 * PL + 7 * PS + 9 + j]; }
-#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { uint32_t w = g[ST_HDR + 6 * PL + 7 * PS + j]; s.fh[j] = FrontState<P, SPEC>::FIRB ? fir_bias_lanes(w) : w; }
-#endif
 }
 
 template <int P, int SPEC>
@@ -238,13 +211,8 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * PL + 7 * l + j] = pack2(s.wi[l][j], s.wq[l][j]); }
 		g[ST_HDR + 6 * PL + 7 * l + 6] = pack2(s.pi[l], s.pq[l]);
 	}
-#if RXB_FIR_TRANSPOSED
-#pragma unroll
-	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = (uint32_t)s.fa[0][j]; g[ST_HDR + 6 * PL + 7 * PS + 9 + j] = (uint32_t)s.fa[1][j]; }
-#else
 #pragma unroll
 	for (int j = 0; j < 9; j++) { g[ST_HDR + 6 * PL + 7 * PS + j] = FrontState<P, SPEC>::FIRB ? fir_unbias_lanes(s.fh[j]) : s.fh[j]; }
-#endif
 }
 
 // ------------------------------------------------------------------------------ stages
@@ -339,26 +307,6 @@ __device__ __forceinline__ void droop9_packed(uint32_t (&h)[9], const int (&c)[6
 	dq = wrap16(aq >> 15);
 }
 
-// Same filter in transposed form.  The reference's sum  y[n] = sum_j g[j] x[n-9+j],  g = (c1 c2 c3 c4 c5 c4 c3 c2 c1),
-// is evaluated in wrapping int32, so any order of the additions gives the same 32 bits.  A[m] holds what the
-// samples seen so far contribute to y[n+m]:  y[n] = A[0];  then x[n] joins every later output,
-//   A[m] <- A[m+1] + g[8-m] x[n]  (m < 8),   A[8] <- g[0] x[n].
-// One IMAD per tap and component writes each partial sum into the register of its successor: no history to
-// shift, nothing to unpack, and the work sits on the FMA pipe instead of the ALU pipe.
-__device__ __forceinline__ void droop9_transposed(int (&a)[2][9], const int (&c)[6], int &di, int &dq)
-{
-	const int yi = wrap16(a[0][0] >> 15), yq = wrap16(a[1][0] >> 15);
-	const int g[9] = {c[1], c[2], c[3], c[4], c[5], c[4], c[3], c[2], c[1]};
-#pragma unroll
-	for (int m = 0; m < 8; m++) {
-		a[0][m] = add_w(a[0][m + 1], mul_w(g[8 - m], di));
-		a[1][m] = add_w(a[1][m + 1], mul_w(g[8 - m], dq));
-	}
-	a[0][8] = mul_w(g[0], di);
-	a[1][8] = mul_w(g[0], dq);
-	di = yi; dq = yq;
-}
-
 // polar_discriminant (src/rtl_fm.c:476-483); note 3.14159.
 __device__ __noinline__ int disc_std(int cr, int cj)
 {
@@ -420,7 +368,7 @@ __device__ __forceinline__ float rcp_est(float x)
 	return __frcp_rn(x);
 #endif
 }
-__device__ __forceinline__ int fast_atan2_generic(int y, int x)
+__device__ __forceinline__ int fast_atan2_i(int y, int x)
 {
 #if RXB_ATAN_V == 0
 	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
@@ -449,36 +397,6 @@ __device__ __forceinline__ int fast_atan2_generic(int y, int x)
 	}
 	const int ang = sub_w(xneg ? q3 : q1, q);
 	return y < 0 ? neg_w(ang) : ang;
-#endif
-}
-
-// Common case first: with den = |x| + |y| in [1, 2^19) nothing wraps, d := |x| - |y| has |d| <= den, and both
-// branches of the reference reduce to one non-negative quotient Qa = floor(4096 |d| / den):
-//   x >= 0: pi/4 - sgn(d) Qa        x < 0: 3pi/4 + sgn(d) Qa        (C's '/' truncates, so the sign factors out)
-// The fp32 estimate of a quotient <= 4096 is off by < 2^-10, so its truncation is Qa or a neighbour and one
-// remainder decides.  Everything else (int32 wrap-around, x == y == 0) takes the generic path.
-__device__ __forceinline__ int fast_atan2_lean(int y, int x)
-{
-	const int ax = x < 0 ? neg_w(x) : x, ay = y < 0 ? neg_w(y) : y;
-	const int den = add_w(ax, ay);
-	if ((unsigned)sub_w(den, 1) >= (1u << 19) - 1u) { return fast_atan2_generic(y, x); }
-	const int d = ax - ay;
-	const int n = (d < 0 ? -d : d) << 12;                          // <= 2^31 - 4096
-	int q = __float2int_rz(__int2float_rn(n) * rcp_est(__int2float_rn(den)));
-	const int r = sub_w(n, mul_w(q, den));                         // in (-den, 2 den); the product alone may wrap
-	q += (r >> 31) + (r >= den ? 1 : 0);
-	const int m = ~((x ^ d) >> 31);                                // -1: Qa is subtracted (x and d of one sign), 0: added
-	const int ang = (1 << 12) + ((x >> 31) & (1 << 13)) + ((q ^ m) - m);
-	const int sy = y >> 31;
-	return (ang ^ sy) - sy;
-}
-
-__device__ __forceinline__ int fast_atan2_i(int y, int x)
-{
-#if RXB_ATAN_V == 2
-	return fast_atan2_lean(y, x);
-#else
-	return fast_atan2_generic(y, x);
 #endif
 }
 
@@ -513,9 +431,6 @@ __device__ __forceinline__ int deemph_step(const FmDev &c, int avg, int x)
 {
 	int d = x - avg;
 	if (c.a_use_magic) {
-#if RXB_DEEMPH_V
-		if (!c.a_even) { return avg + __mulhi(2 * d + c.a, (int)c.a_magic); }   // see deemph_fast
-#endif
 		int n = d + c.a_half + c.a_K * c.a;
 		if (c.a_even) { n -= (d <= 0) ? 1 : 0; }
 		return avg + (int)__umulhi((unsigned)n, c.a_magic) - c.a_K;
@@ -568,7 +483,6 @@ struct Spec {
 
 struct EmitCtx {
 	int16_t *pcm;            // shared PCM buffer
-	uint32_t pcm_sa;         // the same as a shared-window byte address
 	int16_t *out;            // channel output (direct_out only)
 	long long m_lo;          // decimated index of pcm[0]
 	int rel;                 // decimated index of the next sample, relative to m_lo
@@ -586,11 +500,7 @@ template <int P, int SPEC, bool STORE>
 __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, FrontState<P, SPEC> &s, EmitCtx &e, int di, int dq)
 {
 	if (c.fir_on) {
-#if RXB_FIR_TRANSPOSED
-		droop9_transposed(s.fa, c.fir, di, dq);
-#else
 		if constexpr (FrontState<P, SPEC>::FIRB) { droop9_packed(s.fh, c.fir, c.fir_bias, di, dq); } else { droop9(s.fh, c.fir, di, dq); }
-#endif
 	}
 	if (SPEC == 2) {
 		if (k.reduce_mode == 1) {       // rms() inputs of this chunk (src/rtl_fm.c:746-751)
@@ -634,14 +544,7 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 	}
 	if (STORE) {      // the int16 store is the reference's (int16_t) cast
 		if (Spec<SPEC>::direct(k)) { if (SPEC != 2 || k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
-		else {
-#if RXB_PCM_SADDR
-			// generic-pointer stores make ptxas rebuild the window base (S2UR/UMOV/ULEA) in every block
-			asm volatile("st.shared.u16 [%0], %1;" ::"r"(e.pcm_sa + 2u * (uint32_t)pcm_phys(e.rel)), "h"((short)pcm) : "memory");
-#else
-			e.pcm[pcm_phys(e.rel)] = (int16_t)pcm;
-#endif
-		}
+		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
 	}
 	e.rel++;
 }
@@ -780,25 +683,9 @@ __device__ __forceinline__ long long group_start(const FmDev &c, long long o, in
 
 // deemph_filter step on the magic-reciprocal path with the loop-invariant part folded into xb:
 //   xb = x + a/2 + K*a;   avg' = avg + umulhi(xb - avg - [a even && x <= avg], magic) - K
-// Odd a (RXB_DEEMPH_V): c = h always and floor(n / a) == floor((2n + 1) / 2a), where the half-step keeps the
-// argument away from the integers by 1/2a -- more than the error of a truncated reciprocal -- so ONE signed
-// multiply-high is the floor for either sign of n, without bias or correction (host-verified over the range):
-//   xb = 2 x + a;   avg' = avg + mulhi(xb - 2 avg, floor(2^32 / 2a))
-// i.e. an IMAD and an IMAD.HI with avg as the addend: two dependent instructions per step instead of three.
-template <bool EVEN>
-__device__ __forceinline__ int deemph_pre(int x, int bias, int a)
-{
-#if RXB_DEEMPH_V
-	if (!EVEN) { return 2 * x + a; }
-#endif
-	return x + bias;
-}
 template <bool EVEN>
 __device__ __forceinline__ int deemph_fast(int avg, int x, int xb, unsigned magic, int K)
 {
-#if RXB_DEEMPH_V
-	if (!EVEN) { return avg + __mulhi(xb - 2 * avg, (int)magic); }
-#endif
 	int n = xb - avg;
 	if (EVEN) { n -= (x <= avg) ? 1 : 0; }
 	return avg + (int)__umulhi((unsigned)n, magic) - K;
@@ -819,29 +706,29 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
 		for (; (m & 3) != 0 && m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
-			hi = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
+			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
 		}
 #pragma unroll 2
 		for (; m + 4 <= m_end; m += 4) {
 			const int16_t *q = pcm_s + pcm_phys(m);
 			const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
-			lo = deemph_fast<EVEN>(lo, x0, deemph_pre<EVEN>(x0, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x0, deemph_pre<EVEN>(x0, bias, c.a), magic, K);
-			lo = deemph_fast<EVEN>(lo, x1, deemph_pre<EVEN>(x1, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x1, deemph_pre<EVEN>(x1, bias, c.a), magic, K);
-			lo = deemph_fast<EVEN>(lo, x2, deemph_pre<EVEN>(x2, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x2, deemph_pre<EVEN>(x2, bias, c.a), magic, K);
-			lo = deemph_fast<EVEN>(lo, x3, deemph_pre<EVEN>(x3, bias, c.a), magic, K); hi = deemph_fast<EVEN>(hi, x3, deemph_pre<EVEN>(x3, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x0, x0 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x0, x0 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x1, x1 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x1, x1 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x2, x2 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x2, x2 + bias, magic, K);
+			lo = deemph_fast<EVEN>(lo, x3, x3 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x3, x3 + bias, magic, K);
 		}
 		for (; m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
-			hi = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K);
+			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
+			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
 		}
 #else
 		int x = pcm_load(pcm_s, m);
 #pragma unroll 4
 		for (; m < m_end; m++) {
 			int xn = pcm_load(pcm_s, m + 1 < m_end ? m + 1 : m);
-			int xb = deemph_pre<EVEN>(x, bias, c.a);
+			int xb = x + bias;
 			lo = deemph_fast<EVEN>(lo, x, xb, magic, K);
 			hi = deemph_fast<EVEN>(hi, x, xb, magic, K);
 			x = xn;
@@ -868,7 +755,7 @@ __device__ __forceinline__ int back_probe(const FmDev &c, const int16_t *pcm_s, 
 	for (; m < m_end; m++) {
 		const int x = pcm_load(pcm_s, m);
 		int nl, nh;
-		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); nh = deemph_fast<EVEN>(hi, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); }
+		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, x + bias, magic, K); nh = deemph_fast<EVEN>(hi, x, x + bias, magic, K); }
 		else { nl = deemph_step(c, lo, x); nh = deemph_step(c, hi, x); }
 		moved |= (nl ^ lo) | (nh ^ hi);
 		lo = nl; hi = nh;
@@ -933,7 +820,7 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 		}
 		for (int j = 0; j < len; j++) {
 			int xn = pcm_load(pcm_s, m + 1);      // one entry of slack exists past the last sample
-			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, deemph_pre<EVEN>(x, bias, c.a), magic, K); x = wrap16(avg); }
+			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, x + bias, magic, K); x = wrap16(avg); }
 			else if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
 			if (ax) { x = adc_apply(c, *ax, m, x); }
 			acc = add_w(acc, x);
@@ -1067,7 +954,7 @@ __device__ __forceinline__ Item make_item(const FmDev &c, const FmCall &k, int w
 	return it;
 }
 
-// ---- front end of one work item: one segment per thread (tid 0..FM_THREADS-1)
+// ---- front end of one work item: one segment per thread (tid 0..T-1)
 template <int P, int SPEC>
 __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, const Item &it, int tid, int16_t *pcm_s)
 {
@@ -1088,11 +975,7 @@ __device__ __forceinline__ void front_item(const FmDev &c, const FmCall &k, cons
 	unsigned u = (unsigned)(t0 % k.chunk);
 	const long long m0 = dec_before(c, t0, it.box_n0);
 	EmitCtx e;
-	e.pcm = pcm_s; e.pcm_sa = (uint32_t)__cvta_generic_to_shared(pcm_s);
-#if RXB_PCM_SADDR
-	asm volatile("" : "+r"(e.pcm_sa));   // opaque: otherwise the window base is rematerialised at every store
-#endif
-	e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
+	e.pcm = pcm_s; e.out = k.out + (size_t)it.ch * (size_t)k.out_stride; e.m_lo = it.m_lo;
 	e.rel = (int)(m0 - it.m_lo);
 	e.first_in_chunk = 0;
 	if (P == 0) { e.first_in_chunk = (dec_raw(c, t0 - u, it.box_n0) == dec_raw(c, t0, it.box_n0)) ? 1 : 0; }
@@ -1287,11 +1170,12 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	}
 }
 
-// Persistent CTA of 256 threads: all warps run the front end of a work item, then the first
+// Persistent CTA of T threads: all warps run the front end of a work item, then the first
 // `be_lanes/32` warps run the back end out of the shared PCM buffer.  Work items are handed out by an
 // atomic ticket, oldest first (the cross-item look-back only ever waits for an older ticket).
-template <int P, int SPEC>
-__global__ void __launch_bounds__(FM_THREADS, FM_OCC_SCALE * (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1)))) fm_fused_kernel(const FmDev c, const FmCall k)
+// The occupancy target is stated for 256 threads and scales with the width (same threads per SM).
+template <int P, int SPEC, int T>
+__global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3 ? 2 : 1) : (P <= 3 ? RXB_OCC : (P <= 6 ? 2 : 1)))) fm_fused_kernel(const FmDev c, const FmCall k)
 {
 	extern __shared__ __align__(16) int16_t pcm_s[];
 	__shared__ int s_work;
@@ -1405,52 +1289,48 @@ __global__ void fm_adc_recur_kernel(const long long *sums, const int *pcm_len, i
 }
 
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
-static fm_kernel_fn pick_kernel(int P, int spec)
+
+// CTA width.  Measured on B200 (profiles/r1_ab/): the decimating shapes run faster with 128-thread CTAs at the same
+// threads per SM (fm2b +2.6 %, fm5a +61 %), the D = 1 shapes with 256 (fm2a -12 %, fm1 -9 % at 128).  Only the
+// boxcar kernels (P = 0) exist in both widths; RXB200_FM_THREADS overrides the choice there (A/B runs).
+static int fm_cta_threads(int P, int D)
 {
-#ifdef RXB_QUICK   // development builds: only the wbfm P=3 kernel is instantiated (seconds instead of minutes)
-	return (spec == 1 && P == 3) ? fm_fused_kernel<3, 1> : nullptr;
+	if (P > 0) { return 128; }
+	const char *e = getenv("RXB200_FM_THREADS");
+	if (e && (atoi(e) == 128 || atoi(e) == 256)) { return atoi(e); }
+	return D >= 8 ? 128 : 256;
+}
+
+template <int SPEC>
+static fm_kernel_fn pick_kernel_p(int P, int threads)
+{
+#ifdef RXB_QUICK   // development builds: only the wbfm P = 3 kernel is instantiated (seconds instead of minutes)
+	return (SPEC == 1 && P == 3) ? fm_fused_kernel<3, 1, 128> : nullptr;
 #else
-	if (spec == 1) {
-		switch (P) {
-		case 0: return fm_fused_kernel<0, 1>;
-		case 1: return fm_fused_kernel<1, 1>;
-		case 2: return fm_fused_kernel<2, 1>;
-		case 3: return fm_fused_kernel<3, 1>;
-		case 4: return fm_fused_kernel<4, 1>;
-		default: break;
-		}
-	}
-	if (spec == 2) {
-		switch (P) {
-		case 0: return fm_fused_kernel<0, 2>;
-		case 1: return fm_fused_kernel<1, 2>;
-		case 2: return fm_fused_kernel<2, 2>;
-		case 3: return fm_fused_kernel<3, 2>;
-		case 4: return fm_fused_kernel<4, 2>;
-		case 5: return fm_fused_kernel<5, 2>;
-		case 6: return fm_fused_kernel<6, 2>;
-		case 7: return fm_fused_kernel<7, 2>;
-		case 8: return fm_fused_kernel<8, 2>;
-		case 9: return fm_fused_kernel<9, 2>;
-		case 10: return fm_fused_kernel<10, 2>;
-		default: return nullptr;
-		}
-	}
+	constexpr int PMAX = (SPEC == 1) ? 4 : 10;       // the wbfm specialisation is only built for the passes rx_fm can derive for it
+	if (P > PMAX) { return nullptr; }
 	switch (P) {
-	case 0: return fm_fused_kernel<0, 0>;
-	case 1: return fm_fused_kernel<1, 0>;
-	case 2: return fm_fused_kernel<2, 0>;
-	case 3: return fm_fused_kernel<3, 0>;
-	case 4: return fm_fused_kernel<4, 0>;
-	case 5: return fm_fused_kernel<5, 0>;
-	case 6: return fm_fused_kernel<6, 0>;
-	case 7: return fm_fused_kernel<7, 0>;
-	case 8: return fm_fused_kernel<8, 0>;
-	case 9: return fm_fused_kernel<9, 0>;
-	case 10: return fm_fused_kernel<10, 0>;
+	case 0: return threads == 128 ? fm_fused_kernel<0, SPEC, 128> : fm_fused_kernel<0, SPEC, 256>;
+	case 1: return fm_fused_kernel<1, SPEC, 128>;
+	case 2: return fm_fused_kernel<2, SPEC, 128>;
+	case 3: return fm_fused_kernel<3, SPEC, 128>;
+	case 4: return fm_fused_kernel<4, SPEC, 128>;
+	case 5: return fm_fused_kernel<(SPEC == 1 ? 4 : 5), SPEC, 128>;
+	case 6: return fm_fused_kernel<(SPEC == 1 ? 4 : 6), SPEC, 128>;
+	case 7: return fm_fused_kernel<(SPEC == 1 ? 4 : 7), SPEC, 128>;
+	case 8: return fm_fused_kernel<(SPEC == 1 ? 4 : 8), SPEC, 128>;
+	case 9: return fm_fused_kernel<(SPEC == 1 ? 4 : 9), SPEC, 128>;
+	case 10: return fm_fused_kernel<(SPEC == 1 ? 4 : 10), SPEC, 128>;
 	default: return nullptr;
 	}
 #endif
+}
+
+static fm_kernel_fn pick_kernel(int P, int spec, int threads)
+{
+	if (spec == 1 && P <= 4) { return pick_kernel_p<1>(P, threads); }
+	if (spec == 2) { return pick_kernel_p<2>(P, threads); }
+	return pick_kernel_p<0>(P, threads);
 }
 
 }  // namespace rxb
@@ -1493,6 +1373,7 @@ struct rxb200_fm {
 	int tune_seg, tune_warm;
 	rxb200_fm_stats stats;
 	fm_kernel_fn kern;
+	int threads;                   // CTA width of kern
 	int wide;                      // all-scalar fifth_order passes (raw DC block on)
 	int smem_optin;
 	// per-chunk reduction stages
@@ -1542,22 +1423,6 @@ static void fm_fill_dev(rxb200_fm *h)
 			if ((unsigned)(((unsigned long long)n * magic) >> 32) != n / (unsigned)d.a) { ok = false; }
 		}
 		if (ok) { d.a_use_magic = 1; d.a_magic = magic; d.a_K = K; }
-#if RXB_DEEMPH_V
-		if (!d.a_even) {
-			// signed form for odd a: mulhi(2n + 1, floor(2^32 / 2a)) == floor(n / a) for every numerator d + h in range
-			d.a_use_magic = 0;
-			if (d.a >= 3) {
-				const long long m2 = 0x100000000LL / (2LL * d.a);
-				const int lim = 65536 + 32768 + d.a;
-				bool ok2 = true;
-				for (int n = -lim; n <= lim && ok2; n++) {
-					const long long fl = n >= 0 ? n / d.a : -((-(long long)n + d.a - 1) / d.a);
-					if ((((2LL * n + 1) * m2) >> 32) != fl) { ok2 = false; }
-				}
-				if (ok2) { d.a_use_magic = 1; d.a_magic = (unsigned)m2; d.a_K = 0; }
-			}
-		}
-#endif
 	}
 	d.resample = (p.rate_out2 > 0 && p.mode != RXB200_MODE_RAW) ? 1 : 0;
 	d.fast = p.rate_out; d.slow = p.rate_out2; d.lpr_div = d.resample ? (p.rate_out / p.rate_out2) : 1;
@@ -1592,8 +1457,10 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		const bool plain = !params->squelch_level && !params->dc_block_audio && !params->dc_block_raw && params->post_downsample <= 1;
 		const int spec = h->wide ? 2 : ((params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
 		                                 !params->offset_tuning && serial && plain) ? 1 : 0);
-		h->kern = pick_kernel(params->downsample_passes, spec);
+		h->threads = fm_cta_threads(params->downsample_passes, params->downsample);
+		h->kern = pick_kernel(params->downsample_passes, spec, h->threads);
 	}
+	if (!h->kern) { set_error("no kernel for downsample_passes %d in this build", params->downsample_passes); delete h->h_lens; delete h; return RXB200_EUNSUPPORTED; }
 	cudaDeviceProp prop;
 	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
 	h->n_sm = prop.multiProcessorCount;
@@ -1727,6 +1594,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const rxb200_fm_params &p = h->p;
 	const FmDev &dv = h->dev;
 	const long long n = (long long)(n_int16 / 2);
+	const int T = h->threads;
 	const int P = p.downsample_passes;
 	const long long Dtot = dv.D;
 	const long long G = (1LL << P) > 8 ? (1LL << P) : 8;
@@ -1756,11 +1624,11 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	auto geometry = [&](long long sf) -> bool {
 		n_extra = direct_out ? 0 : (margin_dec * Dpcm + halo + sf - 1) / sf;
 		ppt = sf / Dpcm + 2;
-		pcm_cap = direct_out ? 8 : (long long)FM_THREADS * ppt + 64;
+		pcm_cap = direct_out ? 8 : (long long)T * ppt + 64;
 		pcm_cap += 2 * (pcm_cap >> 7) + 8;
 		smem = (size_t)pcm_cap * sizeof(int16_t);
-		if ((long long)smem > h->smem_optin || n_extra > FM_THREADS / 2) { return false; }
-		n_own = FM_THREADS - n_extra;
+		if ((long long)smem > h->smem_optin || n_extra > T / 2) { return false; }
+		n_own = T - n_extra;
 		stretch = n_own * sf;
 		n_cta = (n + stretch - 1) / stretch;
 		return true;
@@ -1779,7 +1647,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	}
 	RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 1;
-	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, T, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	if (!sf_forced) {
 		// tail balancing: work items are handed out to n_sm*per_sm resident CTAs; prefer a slightly shorter
@@ -1791,7 +1659,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 			if (!geometry(sf)) { continue; }
 			double waves = (double)(n_cta * h->n_channels) / slots;
 			double cost = (waves <= 1.0 ? 1.0 : ceil(waves) / waves) * (1.0 + (double)halo / (double)sf) *
-			              ((double)FM_THREADS / (double)n_own);
+			              ((double)T / (double)n_own);
 			if (cost < best_cost - 1e-9) { best_cost = cost; best = sf; }
 		}
 		Sf = best;
@@ -1819,14 +1687,14 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		int bl = e ? atoi(e) : (int)want;
 		bl = (bl / 32) * 32;
 		if (bl < 32) { bl = 32; }
-		if (bl > FM_THREADS) { bl = FM_THREADS; }
+		if (bl > T) { bl = T; }
 		k.be_lanes = bl;
 	}
 	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
 	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
 	const int n_chunks = (int)((n + k.chunk - 1) / k.chunk);
 	k.n_chunks = n_chunks;
-	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, FM_THREADS, smem));
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, T, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	size_t blocks = (size_t)h->n_sm * per_sm;
 	if (blocks > total_work) { blocks = total_work; }
@@ -1835,7 +1703,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		k.reduce_mode = reduce_mode; k.one = 1;
 		RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
 		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev0, h->stream)); }
-		h->kern<<<(unsigned)blocks, FM_THREADS, smem, h->stream>>>(dv, k);
+		h->kern<<<(unsigned)blocks, T, smem, h->stream>>>(dv, k);
 		RXB_CUDA(cudaGetLastError());
 		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev1, h->stream)); }
 		launches++;
@@ -1911,7 +1779,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		if (rc2 != RXB200_OK) { return rc2; }
 	}
 	h->cur ^= 1;
-	h->stats.launches = launches; h->stats.segments = (int)(total_work * FM_THREADS); h->stats.segment_len = (int)Sf;
+	h->stats.launches = launches; h->stats.segments = (int)(total_work * T); h->stats.segment_len = (int)Sf;
 	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1;
 	return RXB200_OK;
 }

@@ -39,14 +39,15 @@ if [ "$WIN" != base ]; then cp rx_tools_b200/variants/librxb200_$WIN.so rx_tools
 timeout 300 python -m pytest tests -x -q -m gpu > $OUT/gpu_tests_final.txt 2>&1; echo "full suite rc=$? t=$((SECONDS-T0))"; tail -2 $OUT/gpu_tests_final.txt
 timeout 120 python __graft_entry__.py smoke > $OUT/smoke.txt 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.txt
 timeout 240 python bench.py > $OUT/bench_fm2b_final.json 2> $OUT/bench_fm2b_final.err; echo "final bench rc=$? t=$((SECONDS-T0))"
-for w in fm2a fm1 fm5a; do
-	timeout 120 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${w}_final.json 2> $OUT/bench_${w}_final.err; echo "$w rc=$?"
-done
 # ---- ncu: launch list of the bench command, one full capture of the fused kernel
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_fm2b.csv \
 	python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_launch_run.log 2>&1; echo "ncu launches rc=$? t=$((SECONDS-T0))"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fm_fused -c 1 -o $OUT/prof_fm2b -f \
 	python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_full_run.log 2>&1; echo "ncu full rc=$? t=$((SECONDS-T0))"
+# ---- the other rx_fm shapes on the winner
+for w in fm2a fm1 fm5a; do
+	timeout 120 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${w}_final.json 2> $OUT/bench_${w}_final.err; echo "$w rc=$?"
+done
 # ---- run-time knobs of the winner (replay length, back-end lanes)
 timeout 200 python tools/ab_sweep.py > $OUT/sweep.txt 2>&1; echo "sweep rc=$? t=$((SECONDS-T0))"; cat $OUT/sweep.txt
 date

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Static instruction mix of the front-end STORE loop of fm_fused_kernel<P,SPEC> (the loop that holds
 the PCM STS.U16 and the 256-bit stream load).  The kernel is integer-issue bound, so this count is the
-first thing to look at before spending GPU time:  tools/sass_loop.py fm_kernels.o [P SPEC]"""
+first thing to look at before spending GPU time:  tools/sass_loop.py fm_kernels.o [P SPEC [WIDTH]]"""
 import collections
 import re
 import subprocess
@@ -14,8 +14,8 @@ ALU = ("SHF", "LEA", "LOP3", "VIADD", "ISETP", "IADD3", "PRMT", "MOV", "SEL", "I
 
 def main():
     obj = sys.argv[1]
-    P, spec = (sys.argv[2], sys.argv[3]) if len(sys.argv) > 3 else ("3", "1")
-    fun = "_ZN3rxb15fm_fused_kernelILi%sELi%sEEEvNS_5FmDevENS_6FmCallE" % (P, spec)
+    P, spec, width = (sys.argv[2:5] + ["128"])[:3] if len(sys.argv) > 3 else ("3", "1", "128")
+    fun = "_ZN3rxb15fm_fused_kernelILi%sELi%sELi%sEEEvNS_5FmDevENS_6FmCallE" % (P, spec, width)
     txt = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
     ins = []
     for line in txt.splitlines():
