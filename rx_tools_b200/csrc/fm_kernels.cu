@@ -1290,37 +1290,39 @@ __global__ void fm_adc_recur_kernel(const long long *sums, const int *pcm_len, i
 
 typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
 
-// CTA width.  Measured on B200 (profiles/r1_ab/): the decimating shapes run faster with 128-thread CTAs at the same
-// threads per SM (fm2b +2.6 %, fm5a +61 %), the D = 1 shapes with 256 (fm2a -12 %, fm1 -9 % at 128).  Only the
-// boxcar kernels (P = 0) exist in both widths; RXB200_FM_THREADS overrides the choice there (A/B runs).
+// CTA width.  Measured on B200 (profiles/r1_ab/): at the same threads per SM the decimating shapes run faster with
+// 128-thread CTAs (fm2b +2.6 %, fm5a +61 %; 64 / 96 / 192 threads lose 21 / 19 / 6 % on fm2b), the D = 1 shapes with
+// 256 (fm2a, fm1: -5 .. -12 % at 128); the boxcar sweep (width_sweep.txt) crosses over between D = 2 and D = 4.
+// Only the boxcar kernels (P = 0) exist in both widths; RXB200_FM_THREADS overrides the choice there (A/B runs).
+#define FM_WIDTH_DECIM 128
 static int fm_cta_threads(int P, int D)
 {
-	if (P > 0) { return 128; }
+	if (P > 0) { return FM_WIDTH_DECIM; }
 	const char *e = getenv("RXB200_FM_THREADS");
 	if (e && (atoi(e) == 128 || atoi(e) == 256)) { return atoi(e); }
-	return D >= 8 ? 128 : 256;
+	return D >= 3 ? 128 : 256;
 }
 
 template <int SPEC>
 static fm_kernel_fn pick_kernel_p(int P, int threads)
 {
 #ifdef RXB_QUICK   // development builds: only the wbfm P = 3 kernel is instantiated (seconds instead of minutes)
-	return (SPEC == 1 && P == 3) ? fm_fused_kernel<3, 1, 128> : nullptr;
+	return (SPEC == 1 && P == 3) ? fm_fused_kernel<3, 1, FM_WIDTH_DECIM> : nullptr;
 #else
 	constexpr int PMAX = (SPEC == 1) ? 4 : 10;       // the wbfm specialisation is only built for the passes rx_fm can derive for it
 	if (P > PMAX) { return nullptr; }
 	switch (P) {
 	case 0: return threads == 128 ? fm_fused_kernel<0, SPEC, 128> : fm_fused_kernel<0, SPEC, 256>;
-	case 1: return fm_fused_kernel<1, SPEC, 128>;
-	case 2: return fm_fused_kernel<2, SPEC, 128>;
-	case 3: return fm_fused_kernel<3, SPEC, 128>;
-	case 4: return fm_fused_kernel<4, SPEC, 128>;
-	case 5: return fm_fused_kernel<(SPEC == 1 ? 4 : 5), SPEC, 128>;
-	case 6: return fm_fused_kernel<(SPEC == 1 ? 4 : 6), SPEC, 128>;
-	case 7: return fm_fused_kernel<(SPEC == 1 ? 4 : 7), SPEC, 128>;
-	case 8: return fm_fused_kernel<(SPEC == 1 ? 4 : 8), SPEC, 128>;
-	case 9: return fm_fused_kernel<(SPEC == 1 ? 4 : 9), SPEC, 128>;
-	case 10: return fm_fused_kernel<(SPEC == 1 ? 4 : 10), SPEC, 128>;
+	case 1: return fm_fused_kernel<1, SPEC, FM_WIDTH_DECIM>;
+	case 2: return fm_fused_kernel<2, SPEC, FM_WIDTH_DECIM>;
+	case 3: return fm_fused_kernel<3, SPEC, FM_WIDTH_DECIM>;
+	case 4: return fm_fused_kernel<4, SPEC, FM_WIDTH_DECIM>;
+	case 5: return fm_fused_kernel<(SPEC == 1 ? 4 : 5), SPEC, FM_WIDTH_DECIM>;
+	case 6: return fm_fused_kernel<(SPEC == 1 ? 4 : 6), SPEC, FM_WIDTH_DECIM>;
+	case 7: return fm_fused_kernel<(SPEC == 1 ? 4 : 7), SPEC, FM_WIDTH_DECIM>;
+	case 8: return fm_fused_kernel<(SPEC == 1 ? 4 : 8), SPEC, FM_WIDTH_DECIM>;
+	case 9: return fm_fused_kernel<(SPEC == 1 ? 4 : 9), SPEC, FM_WIDTH_DECIM>;
+	case 10: return fm_fused_kernel<(SPEC == 1 ? 4 : 10), SPEC, FM_WIDTH_DECIM>;
 	default: return nullptr;
 	}
 #endif

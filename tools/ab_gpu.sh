@@ -3,7 +3,7 @@
 # `-m gpu` suite, the bench lines and the ncu captures on the fastest build that is parity-green.
 # Everything lands in gpurun_out/ab/ as it is produced (the session may be cut short).
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/ab; mkdir -p $OUT
+OUT=${AB_OUT:-gpurun_out/ab}; export OUT; mkdir -p $OUT
 exec > >(tee $OUT/session.log) 2>&1
 date; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 python -c "import torch; print(torch.cuda.get_device_name(0))"
@@ -20,11 +20,11 @@ for so in rx_tools_b200/variants/librxb200_*.so; do
 	echo "$v tests rc=$rc bench rc=$? t=$((SECONDS-T0))"
 done
 WIN=$(python - <<'PY'
-import json
+import json, os
 best, bv = "base", 0.0
-for v in open("gpurun_out/ab/green.txt").read().split():
+for v in open(os.environ["OUT"] + "/green.txt").read().split():
     try:
-        val = json.loads(open(f"gpurun_out/ab/bench_{v}.json").read().strip().splitlines()[-1])["value"]
+        val = json.loads(open(os.environ["OUT"] + f"/bench_{v}.json").read().strip().splitlines()[-1])["value"]
     except Exception:
         continue
     print(v, val, file=__import__("sys").stderr)
@@ -48,6 +48,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:fm_f
 for w in fm2a fm1 fm5a; do
 	timeout 120 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${w}_final.json 2> $OUT/bench_${w}_final.err; echo "$w rc=$?"
 done
+# ---- CTA width against the shape (boxcar kernels exist in both widths), front end alone against the full chain
+timeout 300 python tools/width_sweep.py > $OUT/width_sweep.txt 2>&1; echo "width sweep rc=$? t=$((SECONDS-T0))"; cat $OUT/width_sweep.txt
 # ---- run-time knobs of the winner (replay length, back-end lanes)
-timeout 200 python tools/ab_sweep.py > $OUT/sweep.txt 2>&1; echo "sweep rc=$? t=$((SECONDS-T0))"; cat $OUT/sweep.txt
+if [ -n "$AB_KNOBS" ]; then timeout 200 python tools/ab_sweep.py > $OUT/sweep.txt 2>&1; echo "sweep rc=$? t=$((SECONDS-T0))"; cat $OUT/sweep.txt; fi
 date
