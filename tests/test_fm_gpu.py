@@ -62,6 +62,22 @@ def test_fm_small_segments(name, seg, port):
     d.close()
 
 
+@pytest.mark.parametrize("width", [128, 256])
+@pytest.mark.parametrize("name", ["cfg2A", "cfg1_lut", "wbfm_default", "nbfm_D42_lut", "raw_D4"])
+def test_fm_boxcar_both_cta_widths(name, width, port, monkeypatch):
+    """The boxcar (P = 0) kernels are built for 128- and 256-thread CTAs and the library picks by decimation
+    (fm_cta_threads in csrc/fm_kernels.cu); RXB200_FM_THREADS forces one: both must give the reference's bytes."""
+    monkeypatch.setenv("RXB200_FM_THREADS", str(width))
+    case = next(c for c in fm_cases() if c.name == name)
+    x = case.make_input()[: 2 * 262144]
+    want = port.fm_run(case.params, x, case.chunk_int16)
+    d = fm.FmDemod(case.params)
+    got = d.full_demod(x, case.chunk_int16)
+    _compare(case, got, want)
+    assert d.stats()["segments"] % width == 0
+    d.close()
+
+
 def test_fixup_is_exercised(port):
     case = next(c for c in fm_cases() if c.name == "zeros_deemph")
     x = case.make_input()[: 2 * 262144]
