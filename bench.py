@@ -275,7 +275,7 @@ def run_fm(args, rank, local, world):
                                 "fm5a": "256 NBFM channels at 2.4 Msps, boxcar D=100, lut"}[args.workload],
                    "stream_bytes_per_gpu": int(n_ch * n_int16 * 2), "channels_per_gpu": n_ch, "chunk_complex": CHUNK // 2,
                    "input": f"synthetic CS16, {period}-sample seeded period tiled, device-resident for `value`",
-                   "l2": "input (>= 1 GiB per step) is larger than the 126 MB L2", "parallelism": f"replicas x{world}" if n_ch == 1 else f"channels sharded x{world}",
+                   "l2": f"input ({n_ch * n_int16 * 2 / 2**20:.0f} MiB per step) is larger than the 126 MB L2", "parallelism": f"replicas x{world}" if n_ch == 1 else f"channels sharded x{world}",
                    "segment_len": stats["segment_len"], "warmup_len": stats["warmup_len"],
                    "fixup_segments": stats["fixup_segments"]},
         "gpu_launches": stats["launches"] * args.steps,

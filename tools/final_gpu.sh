@@ -18,8 +18,8 @@ for w in fm2b power3; do
 done
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:fm_fused -c 1 -o $OUT/prof_fm2b -f \
 	python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_full_fm2b.log 2>&1; echo "ncu full fm2b rc=$? t=$((SECONDS-T0))"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:fm_fused -c 1 -o $OUT/prof_fm5a -f \
+# without --import-source: a report with the fused kernel's SASS is ~30 MB and gpurun brings back 64 MiB in all
+timeout 200 ncu --set full --clock-control none -k regex:fm_fused -c 1 -o $OUT/prof_fm5a -f \
 	python bench.py --workload fm5a --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_full_fm5a.log 2>&1; echo "ncu full fm5a rc=$? t=$((SECONDS-T0))"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:power_fft -c 1 -o $OUT/prof_power3 -f \
-	python bench.py --workload power3 --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_full_power3.log 2>&1; echo "ncu full power3 rc=$? t=$((SECONDS-T0))"
+ls -la $OUT; du -sh $OUT
 date
