@@ -35,42 +35,10 @@
 namespace rxb {
 
 #define FM_MAX_THREADS 256       // widest CTA; the width is a kernel template parameter (fm_cta_threads picks it)
-#ifndef RXB_L2_CLAMP
-#define RXB_L2_CLAMP 0
-#endif
-#ifndef RXB_L2_MASK
+// stream prefetch into L2 ahead of the register prefetch: every RXB_L2_MASK+1 samples, RXB_L2_AHEAD samples ahead
 #define RXB_L2_MASK 31
-#endif
-#ifndef RXB_L2_AHEAD
 #define RXB_L2_AHEAD 64
-#endif
-#ifndef RXB_OCC
-#define RXB_OCC 3
-#endif
-#ifndef RXB_RCP_APPROX
-#define RXB_RCP_APPROX 1     // fast_atan2: bare MUFU.RCP (the +-1 remainder correction absorbs its 1 ulp)
-#endif
-#ifndef RXB_CHUNK_LOOP
-#define RXB_CHUNK_LOOP 1     // chunk-start bookkeeping in a one-trip loop ptxas cannot if-convert (else: 16 predicated moves per block)
-#endif
-#ifndef RXB_FIR_PACKED
-#define RXB_FIR_PACKED 1     // droop FIR on biased packed history: symmetric taps added two lanes at a time
-#endif
-#ifndef RXB_LOAD_INPLACE
-#define RXB_LOAD_INPLACE 1   // packed passes: next block is loaded into the registers the scale just freed
-#endif
-#ifndef RXB_L0_UNBIASED
-#define RXB_L0_UNBIASED 0    // 1: pass-0 lanes stay signed (q*65536 + i), bias added once per tap; measured 2 % SLOWER on B200
-#endif
-#ifndef RXB_BE_QUADS
-#define RXB_BE_QUADS 1       // back-end replay walks 4-aligned quads of the PCM buffer (one address per 4 samples)
-#endif
-#ifndef RXB_MAIN_UNROLL
-#define RXB_MAIN_UNROLL 1
-#endif
-#ifndef RXB_ATAN_V
-#define RXB_ATAN_V 1
-#endif
+#define RXB_OCC 3                // resident CTAs per SM of the P <= 3 kernels, stated for 256 threads
 #define FM_MAX_PACKED 3          // fifth_order passes run as packed I/Q SWAR (bias keeps lanes unsigned)
 
 // ------------------------------------------------------------------------------ device config
@@ -124,7 +92,6 @@ enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC,
 static inline int fm_packed_levels(int P, int wide) { return wide ? 0 : (P < FM_MAX_PACKED ? P : FM_MAX_PACKED); }
 static inline int fm_state_words(int P, int wide) { int pl = fm_packed_levels(P, wide); return ST_HDR + 6 * pl + 7 * (P - pl) + 9; }
 
-constexpr uint32_t L0_BIAS = RXB_L0_UNBIASED ? 0x00800080u : 0u;   // pass-0 lanes are unbiased in registers; carry words keep the biased format
 constexpr unsigned FIR_B = 16384u;
 // raw int16 lanes <-> lanes biased by FIR_B (no carry between lanes while |v| <= 16383)
 __device__ __forceinline__ uint32_t fir_bias_lanes(uint32_t w) { return (w ^ 0x80008000u) - 0x40004000u; }
@@ -142,7 +109,7 @@ struct FrontState {
 	static constexpr int PS = P - PL;
 	// droop FIR history kept biased (lane = v + FIR_B) when |v| <= 128 << P leaves head-room for the
 	// sum of two lanes: P <= 6 and no raw DC block
-	static constexpr bool FIRB = (RXB_FIR_PACKED != 0) && (SPEC != 2) && (P >= 1) && (P <= 6);
+	static constexpr bool FIRB = (SPEC != 2) && (P >= 1) && (P <= 6);
 	int box_i, box_q, box_n;
 	// packed passes: the last six samples the pass has seen (oldest first), I in the low and Q in
 	// the high half-word, each biased by 128<<level so both lanes stay unsigned
@@ -160,7 +127,7 @@ __device__ __forceinline__ void front_zero(FrontState<P, SPEC> &s)
 #pragma unroll
 	for (int l = 0; l < FrontState<P, SPEC>::PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l) - (l == 0 ? L0_BIAS : 0u); }
+		for (int j = 0; j < 6; j++) { s.h[l][j] = 0x00010001u * (128u << l); }
 	}
 #pragma unroll
 	for (int l = 0; l < FrontState<P, SPEC>::PS; l++) {
@@ -182,7 +149,7 @@ __device__ __forceinline__ void front_load(FrontState<P, SPEC> &s, const uint32_
 #pragma unroll
 	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { s.h[l][j] = g[ST_HDR + 6 * l + j] - (l == 0 ? L0_BIAS : 0u); }
+		for (int j = 0; j < 6; j++) { s.h[l][j] = g[ST_HDR + 6 * l + j]; }
 	}
 #pragma unroll
 	for (int l = 0; l < PS; l++) {
@@ -203,7 +170,7 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 #pragma unroll
 	for (int l = 0; l < PL; l++) {
 #pragma unroll
-		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * l + j] = s.h[l][j] + (l == 0 ? L0_BIAS : 0u); }
+		for (int j = 0; j < 6; j++) { g[ST_HDR + 6 * l + j] = s.h[l][j]; }
 	}
 #pragma unroll
 	for (int l = 0; l < PS; l++) {
@@ -224,19 +191,6 @@ __device__ __forceinline__ uint32_t hb_tap(uint32_t a, uint32_t b, uint32_t c, u
 {
 	uint32_t s = a + f + (b + e) * 5u + (c + d) * 10u;
 	return (s >> 4) & 0x0FFF0FFFu;
-}
-
-// Pass 0 on unbiased lanes w = q * 65536 + i: the weighted sum of such words is Q * 65536 + I with the
-// true signed lane sums, so adding the whole bias 32 * (128 | 128 << 16) once gives the same word
-// hb_tap builds from biased inputs.
-__device__ __forceinline__ uint32_t hb_tap0(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f)
-{
-#if RXB_L0_UNBIASED
-	uint32_t s = a + f + 32u * 0x00800080u + (b + e) * 5u + (c + d) * 10u;
-	return (s >> 4) & 0x0FFF0FFFu;
-#else
-	return hb_tap(a, b, c, d, e, f);
-#endif
 }
 
 // Scalar fifth_order pass for levels >= 3 (values may exceed the packed head-room; int16 wrap kept).
@@ -360,25 +314,12 @@ __device__ __forceinline__ int disc_std_lean(int cr, int cj)
 // overflow, or x == y == 0) takes the generic path.
 __device__ __forceinline__ float rcp_est(float x)
 {
-#if RXB_RCP_APPROX
 	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // <= 1 ulp; the quotient estimate stays within +-1
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // bare MUFU.RCP, <= 1 ulp; the quotient estimate stays within +-1
 	return r;
-#else
-	return __frcp_rn(x);
-#endif
 }
 __device__ __forceinline__ int fast_atan2_i(int y, int x)
 {
-#if RXB_ATAN_V == 0
-	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
-	if (x == 0 && y == 0) { return 0; }
-	int ya0 = y < 0 ? neg_w(y) : y;
-	int ang0;
-	if (x >= 0) { ang0 = sub_w(q1, div_small_quotient(mul_w(q1, sub_w(x, ya0)), add_w(x, ya0))); }
-	else        { ang0 = sub_w(q3, div_small_quotient(mul_w(q1, add_w(x, ya0)), sub_w(ya0, x))); }
-	return y < 0 ? neg_w(ang0) : ang0;
-#else
 	const int q1 = 1 << 12, q3 = 3 * (1 << 12);
 	const int ya = y < 0 ? neg_w(y) : y;
 	const bool xneg = x < 0;
@@ -397,7 +338,6 @@ __device__ __forceinline__ int fast_atan2_i(int y, int x)
 	}
 	const int ang = sub_w(xneg ? q3 : q1, q);
 	return y < 0 ? neg_w(ang) : ang;
-#endif
 }
 
 // polar_disc_lut (src/rtl_fm.c:528-564)
@@ -567,11 +507,7 @@ __device__ __forceinline__ uint32_t scale_rot_pack(uint32_t w, int pos, bool rot
 {
 	int ri, rq;
 	scale_rot(w, pos, rotate, ri, rq);
-#if RXB_L0_UNBIASED
-	return (uint32_t)ri + ((uint32_t)rq << 16);          // == rq * 65536 + ri: linear, so the tap sum is too
-#else
 	return (uint32_t)(ri + 128) + ((uint32_t)(rq + 128) << 16);
-#endif
 }
 
 __device__ __forceinline__ void ldg256(const int16_t *p, uint32_t (&v)[8])
@@ -590,10 +526,10 @@ __device__ __forceinline__ void front_block_packed(const FmDev &c, const FmCall 
 		// pass 0: window for the sample at block offset 2j is s[2j-5 .. 2j] of (h[0] .. , x[0..7])
 		uint32_t (&h0)[6] = s.h[0];
 		uint32_t y[4];
-		y[0] = hb_tap0(h0[1], h0[2], h0[3], h0[4], h0[5], x[0]);
-		y[1] = hb_tap0(h0[3], h0[4], h0[5], x[0], x[1], x[2]);
-		y[2] = hb_tap0(h0[5], x[0], x[1], x[2], x[3], x[4]);
-		y[3] = hb_tap0(x[1], x[2], x[3], x[4], x[5], x[6]);
+		y[0] = hb_tap(h0[1], h0[2], h0[3], h0[4], h0[5], x[0]);
+		y[1] = hb_tap(h0[3], h0[4], h0[5], x[0], x[1], x[2]);
+		y[2] = hb_tap(h0[5], x[0], x[1], x[2], x[3], x[4]);
+		y[3] = hb_tap(x[1], x[2], x[3], x[4], x[5], x[6]);
 #pragma unroll
 		for (int j = 0; j < 6; j++) { h0[j] = x[j + 2]; }
 		uint32_t outw[4];
@@ -702,7 +638,6 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
 	if (c.a_use_magic) {
-#if RXB_BE_QUADS
 		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
 		for (; (m & 3) != 0 && m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
@@ -723,17 +658,6 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
 			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
 		}
-#else
-		int x = pcm_load(pcm_s, m);
-#pragma unroll 4
-		for (; m < m_end; m++) {
-			int xn = pcm_load(pcm_s, m + 1 < m_end ? m + 1 : m);
-			int xb = x + bias;
-			lo = deemph_fast<EVEN>(lo, x, xb, magic, K);
-			hi = deemph_fast<EVEN>(hi, x, xb, magic, K);
-			x = xn;
-		}
-#endif
 	} else {
 		for (; m < m_end; m++) {
 			const int x = pcm_load(pcm_s, m);
@@ -763,12 +687,6 @@ __device__ __forceinline__ int back_probe(const FmDev &c, const int16_t *pcm_s, 
 	return moved;
 }
 
-// Outputs [oa, ob) of one lane from an exact state: per output, de-emphasise the group's samples,
-// sum them and divide by the integer rate ratio (deemph_filter :673-680, low_pass_real :396-407).
-// `phase` is the resampler phase at the first group's start; right after an emission it is < slow, so a
-// group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
-// group a call inherits from the previous call can start with a larger phase).
-// m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
 // audio DC block bookkeeping of one back-end lane (dc_block_audio_filter, src/rtl_fm.c:684-697)
 struct AdcCtx {
 	const int *adc;          // per-chunk average to subtract (null: stage off or pre-pass)
@@ -875,26 +793,18 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
                                           const int16_t *__restrict__ in, int t, int t_end, int t_last, unsigned &u, int ch)
 {
 	if (t >= t_end) { return; }
-	constexpr bool INPLACE = (RXB_LOAD_INPLACE != 0) && (FrontState<P, SPEC>::PL > 0);
+	constexpr bool INPLACE = FrontState<P, SPEC>::PL > 0;   // packed passes: the next block is loaded into the registers the scale just freed
 	uint32_t v[8], vn[8];
 	ldg256(in + 2 * (size_t)t, v);
-#if RXB_MAIN_UNROLL == 2
-#pragma unroll 2
-#elif RXB_MAIN_UNROLL == 3
-#pragma unroll 3
-#endif
 	for (; t < t_end; t += 8) {
 		const int tn = t + 8 <= t_last ? t + 8 : t_last;       // next block, clamped to the segment's last one
 		if constexpr (!INPLACE) { ldg256(in + 2 * (size_t)tn, vn); }
-#if RXB_L2_AHEAD > 0
 		// pull the stream into L2 well ahead of the register prefetch (each thread walks its own region)
 		if ((t & RXB_L2_MASK) == 0) {
-			const int tp = min(t + RXB_L2_AHEAD, t_last + RXB_L2_CLAMP);               // never (far) past the segment
+			const int tp = min(t + RXB_L2_AHEAD, t_last);               // never past the segment
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2 * (size_t)tp));
 		}
-#endif
 		if (u >= (unsigned)k.chunk) { u = 0u; }
-#if RXB_CHUNK_LOOP
 		// a lane meets a chunk start once in chunk/8 blocks.  Left alone, ptxas if-converts the bookkeeping into
 		// ~16 predicated-off moves in EVERY block; a loop (trip count k.one == 1, unknown to the compiler) cannot
 		// be predicated, so the common path pays one branch
@@ -902,9 +812,6 @@ __device__ __forceinline__ void front_run(const FmDev &c, const FmCall &k, Front
 #pragma unroll 1
 			for (int z = 0; z < k.one; z++) { front_chunk_start<P, SPEC, STORE>(c, k, s, e, ch); }
 		}
-#else
-		if (u == 0u) { front_chunk_start<P, SPEC, STORE>(c, k, s, e, ch); }
-#endif
 		if constexpr (INPLACE) {
 			// scale first; the block's registers are free from here on, so the next block is loaded
 			// straight into them and has the whole rest of this block's work to arrive
@@ -1061,9 +968,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		if (active || q == 0) {
 			int ws = p.ga - k.W_dec;
 			if (ws < 0) { ws = 0; }
-#if RXB_BE_QUADS
-			ws &= ~3;           // a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
-#endif
+			ws &= ~3;           // quad-aligned start: a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
 			if (it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
 			if (c.deemph) {
 				if (c.a_even) { back_replay<true>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, p.ga, lo, hi); }

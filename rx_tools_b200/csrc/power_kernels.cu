@@ -67,16 +67,9 @@ __device__ __forceinline__ uint32_t ppack(int re, int im) { return ((uint32_t)re
 // FIX_MPY (src/rtl_power.c:256-262): c = (a*b)>>14; (c>>1)+(c&1)  ==  (a*b + 2^14) >> 15.
 // The int16 truncation of its result and of tr/ti is deferred to the final pack: everything in
 // between is addition modulo 2^16.
-#ifndef RXB_Q15_HI
-#define RXB_Q15_HI 0
-#endif
 __device__ __forceinline__ int q15(int a, int b)
 {
-#if RXB_Q15_HI
-	return __mulhi(a * b + 16384, 1 << 17);      // same value as >> 15, on the multiplier pipe instead of the shifter
-#else
-	return (a * b + 16384) >> 15;
-#endif
+	return (a * b + 16384) >> 15;     // (a mulhi-by-2^17 form on the multiplier pipe instead of the shifter measured slower)
 }
 
 __device__ __forceinline__ long long block_sum(long long v, long long *red, int tid, int nthreads)
@@ -355,11 +348,7 @@ __device__ __forceinline__ void bfly(Cx &lo, Cx &hi, int wr, int wi)
 	const int tr = q15(wr, vr) - q15(wi, vi);
 	const int ti = q15(wr, vi) + q15(wi, vr);
 	// unsigned shift: the wrap is intended (a signed multiply would let the compiler fold it away)
-#if RXB_Q15_HI
-	const int qr = __mulhi((int)((unsigned)lo.re << 16), 1 << 15), qi = __mulhi((int)((unsigned)lo.im << 16), 1 << 15);
-#else
 	const int qr = (int)((unsigned)lo.re << 16) >> 17, qi = (int)((unsigned)lo.im << 16) >> 17;
-#endif
 	hi.re = qr - tr;
 	hi.im = qi - ti;
 	lo.re = qr + tr;
