@@ -16,7 +16,7 @@
 #define REP8(x) x x x x x x x x
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k(uint32_t *out, long long *cyc, int iters, uint32_t m, uint32_t a)
+__global__ void __launch_bounds__(1024) k(uint32_t *out, long long *cyc, int iters, uint32_t m, uint32_t a)
 {
 	uint32_t f0 = threadIdx.x, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3, f4 = f0 + 4, f5 = f0 + 5, f6 = f0 + 6, f7 = f0 + 7;
 	uint32_t l0 = f0 ^ 9, l1 = f1 ^ 9, l2 = f2 ^ 9, l3 = f3 ^ 9, l4 = f4 ^ 9, l5 = f5 ^ 9, l6 = f6 ^ 9, l7 = f7 ^ 9;
@@ -49,21 +49,22 @@ __global__ void __launch_bounds__(128) k(uint32_t *out, long long *cyc, int iter
 	}
 	long long t1 = clock64();
 	out[blockIdx.x * blockDim.x + threadIdx.x] = f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7 + l0 + l1 + l2 + l3 + l4 + l5 + l6 + l7;
-	if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; }
+	if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; }      // warp 0 of the block; all warps of a block share its SM
 }
 
 template <int MODE>
 static double run(int warps_per_sm, int n_sm, uint32_t *out, long long *cyc)
 {
-	// warps_per_sm resident warps: blocks of 32 threads, one wave
-	const int iters = 2000, blocks = warps_per_sm * n_sm;
-	k<MODE><<<blocks, 32>>>(out, cyc, 10, 3u, 7u);
-	k<MODE><<<blocks, 32>>>(out, cyc, iters, 3u, 7u);
+	// ONE block of 32 * warps_per_sm threads per SM (the first version launched single-warp blocks and its rows from
+	// 12 warps/SM on showed more than one instruction per clock: the timed blocks were not sharing their SM with the rest)
+	const int iters = 2000, blocks = n_sm, threads = 32 * warps_per_sm;
+	k<MODE><<<blocks, threads>>>(out, cyc, 10, 3u, 7u);
+	k<MODE><<<blocks, threads>>>(out, cyc, iters, 3u, 7u);
 	cudaDeviceSynchronize();
-	long long h[64];
-	cudaMemcpy(h, cyc, sizeof(long long) * (blocks < 64 ? blocks : 64), cudaMemcpyDeviceToHost);
+	long long h[256];
+	cudaMemcpy(h, cyc, sizeof(long long) * (blocks < 256 ? blocks : 256), cudaMemcpyDeviceToHost);
 	double worst = 0;
-	for (int i = 0; i < (blocks < 64 ? blocks : 64); i++) { if ((double)h[i] > worst) { worst = (double)h[i]; } }
+	for (int i = 0; i < (blocks < 256 ? blocks : 256); i++) { if ((double)h[i] > worst) { worst = (double)h[i]; } }
 	// 256 instructions per iteration per warp; cycles per instruction PER SUB-PARTITION (4 per SM)
 	return worst / ((double)iters * 256.0 * warps_per_sm / 4.0);
 }
@@ -73,7 +74,7 @@ int main()
 	cudaDeviceProp p;
 	cudaGetDeviceProperties(&p, 0);
 	uint32_t *out; long long *cyc;
-	cudaMalloc(&out, sizeof(uint32_t) * 32 * 32 * p.multiProcessorCount);
+	cudaMalloc(&out, sizeof(uint32_t) * 1024 * p.multiProcessorCount);
 	cudaMalloc(&cyc, sizeof(long long) * 32 * p.multiProcessorCount);
 	printf("%s, %d SMs; cycles per warp instruction per sub-partition (1.0 = one issue per clock)\n", p.name, p.multiProcessorCount);
 	printf("warps/SM   runs-of-32   alternating   IMAD-only   ALU-only\n");
