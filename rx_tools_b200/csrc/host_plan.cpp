@@ -47,7 +47,9 @@ extern "C" int rxb200_fm_derive(const rxb200_fm_cli *cli, rxb200_fm_derived *out
 	if (cli->wbfm) {
 		mode = RXB200_MODE_FM;
 		rate_in = 170000; rate_out = 170000; rate_out2 = 32000; output_rate = 32000;
-		custom_atan = RXB200_ATAN_FAST; deemph = 1; squelch = 0;
+		// the preset zeroes squelch_level WHEN -M is parsed (:1339), so a later -l survives: the caller applies that
+		// parse-order rule to cli->squelch_level (host/rx_fm_b200.c does), derive keeps what it is given
+		custom_atan = RXB200_ATAN_FAST; deemph = 1;
 	}
 	if (cli->rate_s > 0) { rate_in = cli->rate_s; rate_out = cli->rate_s; }
 	if (cli->rate_r > 0) { output_rate = cli->rate_r; rate_out2 = cli->rate_r; }

@@ -638,6 +638,16 @@ static int power_validate(const rxb200_power_params *p)
 			set_error("bin_e %d with buf_len %d does not fit shared memory", p->bin_e, p->buf_len);
 			return RXB200_EUNSUPPORTED;
 		}
+		// the block loop runs while offset < buf_len/downsample (src/rtl_power.c:747): a partial last block is
+		// transformed too (over the zeros the decimator left), which only stays inside the hop buffer when the
+		// rounded-up block count does -- the planner's shapes do (:504-507); anything else would run past the buffer
+		{
+			const long long used = p->buf_len / p->downsample, two_n = 2LL << p->bin_e;
+			if (((used + two_n - 1) / two_n) * two_n > p->buf_len) {
+				set_error("buf_len %d / downsample %d: the last %d-point block would end past the hop buffer", p->buf_len, p->downsample, 1 << p->bin_e);
+				return RXB200_EINVAL;
+			}
+		}
 	}
 	return RXB200_OK;
 }

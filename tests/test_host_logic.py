@@ -60,3 +60,11 @@ def test_planner_and_csv_match_reference(ref_power, port):
     mine = power.csv_rows(plan, avg, smp)
     theirs = ref_power.csv("/tmp/_csv_ref.txt")
     assert mine == theirs
+
+
+def test_wbfm_preset_keeps_a_later_squelch_level():
+    """-M wbfm zeroes squelch_level when it is parsed (src/rtl_fm.c:1331-1341); `-M wbfm -l 50` keeps 50.  The parse-order
+    rule lives in the shell (host/rx_fm_b200.c), rxb200_fm_derive passes cli.squelch_level through."""
+    from rx_tools_b200 import fm
+    assert fm.derive_params(wbfm=1, squelch_level=50).params.squelch_level == 50
+    assert fm.derive_params(wbfm=1).params.squelch_level == 0
