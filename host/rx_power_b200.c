@@ -6,6 +6,10 @@
  * hop, one readStream per hop buffer; the window x fix_fft x power-accumulate of every hop of a sweep is
  * ONE rxb200_power_accumulate() call, the report is rxb200_power_read_db() (csv_dbm's arithmetic on the
  * device) + rxb200_power_format_db_row().
+ *
+ * Several GPUs: RXB200_GPUS=n (environment, so the reference's option string stays as it is) shards the hops over
+ * n GPUs of this box through rxb200_power_group_* -- every GPU transforms the hops it owns, ONE NCCL all-gather
+ * collates the spectrum rows in hop order before the report loop (src/rtl_power.c:1047-1050).
  */
 #include <math.h>
 #include <signal.h>
@@ -105,8 +109,13 @@ int main(int argc, char **argv)
 
 	int *window_coefs = (int *)malloc(sizeof(int) * (size_t)N);
 	rxb200_window_table(window, N, window_coefs);
-	rxb200_power *pw = NULL;
-	if (rxb200_power_create(pp, window_coefs, NULL, 0, &pw) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); return 1; }
+	int n_gpus = getenv("RXB200_GPUS") ? atoi(getenv("RXB200_GPUS")) : 1;
+	if (n_gpus < 1) { n_gpus = 1; }
+	if (n_gpus > n_hops) { n_gpus = n_hops; }
+	rxb200_power_group *grp = NULL;
+	if (rxb200_power_group_create(pp, window_coefs, NULL, n_gpus, NULL, &grp) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); return 1; }
+	rxb200_power *pw = rxb200_power_group_member(grp, 0);     /* after the gather member 0 holds every row */
+	if (n_gpus > 1) { fprintf(stderr, "Hops sharded over %d GPUs\n", n_gpus); }
 
 	SoapySDRDevice *dev = NULL; SoapySDRStream *stream = NULL;
 	if (sdr_open(dev_query, channel, &dev, &stream) != 0) { fprintf(stderr, "Failed to open sdr device matching '%s'.\n", dev_query); return 1; }
@@ -160,14 +169,14 @@ int main(int argc, char **argv)
 			if (first_ok < 0) { first_ok = i; }
 			if (i != first_ok + n_ok) {
 				/* a hop in the middle failed: flush the contiguous run gathered so far, start a new one */
-				rxb200_power_accumulate(pw, stage + (size_t)first_ok * buf_len, 1, first_ok, first_ok + n_ok);
+				rxb200_power_group_accumulate(grp, stage + (size_t)first_ok * buf_len, 1, first_ok, first_ok + n_ok);
 				first_ok = i; n_ok = 0;
 			}
 			memcpy(stage + (size_t)i * buf_len, rd, (size_t)buf_len * 2);
 			n_ok++;
 		}
 		if (n_ok > 0) {
-			if (rxb200_power_accumulate(pw, stage + (size_t)first_ok * buf_len, 1, first_ok, first_ok + n_ok) != RXB200_OK) {
+			if (rxb200_power_group_accumulate(grp, stage + (size_t)first_ok * buf_len, 1, first_ok, first_ok + n_ok) != RXB200_OK) {
 				fprintf(stderr, "rxb200: %s\n", rxb200_last_error());
 				break;
 			}
@@ -182,6 +191,7 @@ int main(int argc, char **argv)
 		localtime_r(&now, &cal);
 		strftime(tstr, sizeof tstr, "%Y-%m-%d, %H:%M:%S", &cal);
 		if (getenv("RXB200_FIXED_TIME")) { snprintf(tstr, sizeof tstr, "%s", getenv("RXB200_FIXED_TIME")); }
+		if (rxb200_power_group_gather(grp) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); break; }
 		if (rxb200_power_read_db(pw, plan.rate, plan.crop, db, (size_t)row_len, samples) != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); break; }
 		int have = 0;
 		for (int i = 0; i < n_hops; i++) { have |= samples[i]; }
@@ -195,14 +205,14 @@ int main(int argc, char **argv)
 			}
 			fflush(out);
 		}
-		rxb200_power_reset(pw);
+		rxb200_power_group_reset(grp);
 		while (time(NULL) >= next_tick) { next_tick += interval; }
 		if (single || hooked || stream_dry) { done = 1; }
 		if (exit_time && time(NULL) >= exit_time) { done = 1; }
 	}
 	fprintf(stderr, g_stop ? "\nUser cancel, exiting...\n" : "\nDone, exiting...\n");
 	if (out != stdout) { fclose(out); }
-	rxb200_power_destroy(pw);
+	rxb200_power_group_destroy(grp);
 	sdr_close(dev, stream);
 	return 0;
 }

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RXB200_ABI_VERSION 2
+#define RXB200_ABI_VERSION 3
 
 /* error codes */
 #define RXB200_OK            0
@@ -255,6 +255,42 @@ int rxb200_power_format_db_row(const double *db_row, int bin_e, int64_t freq, in
  * Returns the number of bytes written, or RXB200_ECAPACITY. */
 int rxb200_power_format_row(int64_t *avg_row, int bin_e, int64_t freq, int rate, int downsample,
                             double crop, int samples, char *dst, size_t dst_cap);
+
+/* ======================================================================== rx_power on several GPUs
+ * Tuner hops are independent (one scanner() iteration each, src/rtl_power.c:679-771), so they shard over GPUs:
+ * rank r of n owns the contiguous hops [r*per, (r+1)*per), per = ceil(n_hops/n) (rxb200_power_shard).  The only
+ * exchange is the collation before the report loop (src/rtl_power.c:1047-1050 walks tunes[] in hop order): ONE NCCL
+ * all-gather of the int64 accumulator rows (+ the samples vector), done IN PLACE on the handle's accumulator array,
+ * after which every rank holds every row and rxb200_power_read / _read_db work as on a single GPU.
+ * NCCL is bound at run time (libnccl.so.2); RXB200_EUNSUPPORTED when it cannot be loaded. */
+typedef struct rxb200_comm rxb200_comm;
+#define RXB200_UNIQUE_ID_BYTES 128
+#define RXB200_MAX_RANKS 16
+/* one process per GPU: rank 0 makes the id, the launcher's own transport carries the 128 bytes to the others */
+int rxb200_comm_unique_id(void *id128);
+int rxb200_comm_create(int n_ranks, int rank, const void *id128, int device, rxb200_comm **out);
+/* one process, n_dev GPUs (devices == NULL: 0..n_dev-1): out receives n_dev communicators */
+int rxb200_comm_create_all(int n_dev, const int *devices, rxb200_comm **out);
+void rxb200_comm_destroy(rxb200_comm *c);
+int rxb200_comm_size(const rxb200_comm *c);
+int rxb200_comm_rank(const rxb200_comm *c);
+int rxb200_power_shard(int n_hops, int n_ranks, int rank, int *hop_begin, int *hop_end);
+/* The collation, enqueued on the handle's stream behind its kernels; collective: every rank of the communicator calls
+ * it with a handle of identical parameters that accumulated (only) its own hop range since the last reset. */
+int rxb200_power_gather(rxb200_power *h, rxb200_comm *c, int sync);
+
+/* All ranks inside ONE process (what the drop-in rx_power shell uses): n_dev handles, one per GPU. */
+typedef struct rxb200_power_group rxb200_power_group;
+int rxb200_power_group_create(const rxb200_power_params *params, const int *window_coefs, const int16_t *sinewave,
+                              int n_dev, const int *devices, rxb200_power_group **out);
+void rxb200_power_group_destroy(rxb200_power_group *g);
+int rxb200_power_group_size(const rxb200_power_group *g);
+rxb200_power *rxb200_power_group_member(rxb200_power_group *g, int i);
+/* like rxb200_power_accumulate (HOST hop buffers); each member takes the hops of the range it owns */
+int rxb200_power_group_accumulate(rxb200_power_group *g, const int16_t *hop_bufs, int n_pass, int hop_begin, int hop_end);
+/* the all-gather; afterwards member 0 (every member) reads/reports all hops */
+int rxb200_power_group_gather(rxb200_power_group *g);
+int rxb200_power_group_reset(rxb200_power_group *g);
 
 /* ======================================================================== rx_sdr
  * The pointwise sample-format conversions of rx_sdr's recorder loop (src/rtl_sdr.c:348-391):

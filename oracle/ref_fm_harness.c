@@ -216,22 +216,22 @@ long ref_fm_run_levels(const int16_t *in, size_t n_int16, size_t chunk_int16, in
 	return (long)c;
 }
 
-/* Same loop, timed, output discarded into a scratch ring (for the cpu_baseline / --impl
- * reference legs of bench.py).  Returns seconds. */
+/* Same loop, timed (for the cpu_baseline / --impl reference legs of bench.py).  rtlsdr_callback only reads
+ * its buffer while dongle.mute == 0 (src/rtl_fm.c:839-843), so every chunk is handed over where it lies,
+ * exactly what the dongle thread does with the readStream buffer (:894-899).  Returns seconds. */
 double ref_fm_time(const int16_t *in, size_t n_int16, size_t chunk_int16, int repeats, long *n_out)
 {
-	static int16_t tmp[MAXIMUM_BUF_LENGTH];
 	struct timespec t0, t1;
 	long total = 0;
 	int r;
+	dongle.mute = 0;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	for (r = 0; r < repeats; r++) {
 		size_t pos = 0;
 		while (pos < n_int16) {
 			size_t len = n_int16 - pos;
 			if (len > chunk_int16) { len = chunk_int16; }
-			memcpy(tmp, in + pos, len * 2);
-			rtlsdr_callback(tmp, (uint32_t)len, &dongle);
+			rtlsdr_callback((int16_t *)(in + pos), (uint32_t)len, &dongle);
 			full_demod(&demod);
 			total += demod.result_len;
 			pos += len;

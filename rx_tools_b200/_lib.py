@@ -63,6 +63,10 @@ SYMBOLS = [
     "rxb200_power_device_avg", "rxb200_power_reset", "rxb200_power_stream", "rxb200_power_last_launches",
     "rxb200_power_format_row", "rxb200_power_kernel_ms", "rxb200_power_row_len", "rxb200_power_read_db",
     "rxb200_power_format_db_row",
+    "rxb200_comm_unique_id", "rxb200_comm_create", "rxb200_comm_create_all", "rxb200_comm_destroy", "rxb200_comm_size",
+    "rxb200_comm_rank", "rxb200_power_shard", "rxb200_power_gather",
+    "rxb200_power_group_create", "rxb200_power_group_destroy", "rxb200_power_group_size", "rxb200_power_group_member",
+    "rxb200_power_group_accumulate", "rxb200_power_group_gather", "rxb200_power_group_reset",
     "rxb200_sdr_convert", "rxb200_sdr_convert_device",
 ]
 
@@ -118,6 +122,24 @@ def lib() -> C.CDLL:
     L.rxb200_power_read_db.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), sz, pint]
     L.rxb200_power_format_db_row.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
                                              C.c_int, C.c_char_p, sz]
+    L.rxb200_comm_unique_id.argtypes = [C.c_void_p]
+    L.rxb200_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.rxb200_comm_create_all.argtypes = [C.c_int, pint, C.POINTER(C.c_void_p)]
+    L.rxb200_comm_destroy.argtypes = [C.c_void_p]
+    L.rxb200_comm_destroy.restype = None
+    L.rxb200_comm_size.argtypes = [C.c_void_p]
+    L.rxb200_comm_rank.argtypes = [C.c_void_p]
+    L.rxb200_power_shard.argtypes = [C.c_int, C.c_int, C.c_int, pint, pint]
+    L.rxb200_power_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.rxb200_power_group_create.argtypes = [C.POINTER(PowerParamsC), pint, p16, C.c_int, pint, C.POINTER(C.c_void_p)]
+    L.rxb200_power_group_destroy.argtypes = [C.c_void_p]
+    L.rxb200_power_group_destroy.restype = None
+    L.rxb200_power_group_size.argtypes = [C.c_void_p]
+    L.rxb200_power_group_member.argtypes = [C.c_void_p, C.c_int]
+    L.rxb200_power_group_member.restype = C.c_void_p
+    L.rxb200_power_group_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.rxb200_power_group_gather.argtypes = [C.c_void_p]
+    L.rxb200_power_group_reset.argtypes = [C.c_void_p]
     L.rxb200_sdr_convert.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_int]
     L.rxb200_sdr_convert_device.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p, C.c_void_p]
     _lib = L

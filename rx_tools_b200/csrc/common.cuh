@@ -20,6 +20,18 @@ void set_error(const char *fmt, ...);
 		}                                                                                \
 	} while (0)
 
+// same, running `cleanup` first (create paths: nothing may leak when a CUDA call fails half way)
+#define RXB_CUDA_OR(call, cleanup)                                                       \
+	do {                                                                                 \
+		cudaError_t e__ = (call);                                                        \
+		if (e__ != cudaSuccess) {                                                        \
+			rxb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),      \
+			               __FILE__, __LINE__);                                          \
+			cleanup;                                                                     \
+			return RXB200_ECUDA;                                                         \
+		}                                                                                \
+	} while (0)
+
 // ---- two's-complement helpers: the reference relies on x86 wrap-around for int overflow and
 // on truncating stores to int16_t (SURVEY.md §7 hard part 5); unsigned arithmetic makes the
 // wrap well-defined here.

@@ -18,6 +18,7 @@
 #include <new>
 #include <vector>
 #include "common.cuh"
+#include "nccl_dyn.h"
 
 namespace rxb {
 
@@ -608,11 +609,14 @@ static const int k_cic9_power[11][6] = {
 	{9, -119, -577, 5917, -26067, 77473}, {9, -199, -362, 5303, -25505, 77489},
 };
 
+#define RXB_ROW_PAD 16        // >= the largest communicator size - 1
 struct rxb200_power {
 	rxb200_power_params p;
 	int device;
 	cudaStream_t stream;
-	long long *d_avg;          // [n_hops][N]
+	long long *d_avg;          // [n_hops + RXB_ROW_PAD][N]: the padding rows stay zero; they make the hop rows a whole
+	                           // number of equal per-rank blocks so the all-gather runs in place
+	int *d_samples;            // [n_hops + RXB_ROW_PAD] staging of `samples` for the gather
 	int16_t *d_sine, *d_window;
 	int16_t *d_in; size_t d_in_cap;
 	std::vector<int> samples;  // tunes[i].samples mirror (deterministic, kept on the host)
@@ -665,18 +669,21 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 	RXB_CUDA(cudaSetDevice(device));
 	rxb200_power *h = new (std::nothrow) rxb200_power();
 	if (!h) { return RXB200_ENOMEM; }
-	h->p = *params; h->device = device; h->d_avg = nullptr; h->d_sine = nullptr; h->d_window = nullptr;
+	h->p = *params; h->device = device; h->d_avg = nullptr; h->d_samples = nullptr; h->d_sine = nullptr; h->d_window = nullptr;
 	h->d_in = nullptr; h->d_in_cap = 0; h->launches = 0;
 	h->samples.assign(params->n_hops, 0);
 	cudaDeviceProp prop;
-	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
+	RXB_CUDA_OR(cudaGetDeviceProperties(&prop, device), rxb200_power_destroy(h));
 	h->n_sm = prop.multiProcessorCount;
-	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-	RXB_CUDA(cudaEventCreate(&h->ev0));
-	RXB_CUDA(cudaEventCreate(&h->ev1));
+	RXB_CUDA_OR(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), rxb200_power_destroy(h));
+	RXB_CUDA_OR(cudaEventCreate(&h->ev0), rxb200_power_destroy(h));
+	RXB_CUDA_OR(cudaEventCreate(&h->ev1), rxb200_power_destroy(h));
 	const size_t N = (size_t)1 << params->bin_e;
-	RXB_CUDA(cudaMalloc(&h->d_avg, (size_t)params->n_hops * N * sizeof(long long)));
-	RXB_CUDA(cudaMemset(h->d_avg, 0, (size_t)params->n_hops * N * sizeof(long long)));
+	const size_t rows_cap = (size_t)params->n_hops + RXB_ROW_PAD;
+	RXB_CUDA_OR(cudaMalloc(&h->d_avg, rows_cap * N * sizeof(long long)), rxb200_power_destroy(h));
+	RXB_CUDA_OR(cudaMemset(h->d_avg, 0, rows_cap * N * sizeof(long long)), rxb200_power_destroy(h));
+	RXB_CUDA_OR(cudaMalloc(&h->d_samples, rows_cap * sizeof(int)), rxb200_power_destroy(h));
+	RXB_CUDA_OR(cudaMemset(h->d_samples, 0, rows_cap * sizeof(int)), rxb200_power_destroy(h));
 	if (params->bin_e > 0) {
 		std::vector<int16_t> sine(N * 3 / 4 + 8), win(N);
 		if (sinewave) { memcpy(sine.data(), sinewave, (N * 3 / 4) * sizeof(int16_t)); }
@@ -684,10 +691,10 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 		// (int16)(x * w) depends only on w modulo 2^16, so the table is kept as int16
 		for (size_t i = 0; i < N; i++) { win[i] = (int16_t)window_coefs[i]; }
 		h->triv = (N >= 8 && sine[0] == 0 && (sine[N / 2] == 0 || sine[N / 2] == 1)) ? 1 : 0;
-		RXB_CUDA(cudaMalloc(&h->d_sine, sine.size() * sizeof(int16_t)));
-		RXB_CUDA(cudaMalloc(&h->d_window, win.size() * sizeof(int16_t)));
-		RXB_CUDA(cudaMemcpy(h->d_sine, sine.data(), sine.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
-		RXB_CUDA(cudaMemcpy(h->d_window, win.data(), win.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+		RXB_CUDA_OR(cudaMalloc(&h->d_sine, sine.size() * sizeof(int16_t)), rxb200_power_destroy(h));
+		RXB_CUDA_OR(cudaMalloc(&h->d_window, win.size() * sizeof(int16_t)), rxb200_power_destroy(h));
+		RXB_CUDA_OR(cudaMemcpy(h->d_sine, sine.data(), sine.size() * sizeof(int16_t), cudaMemcpyHostToDevice), rxb200_power_destroy(h));
+		RXB_CUDA_OR(cudaMemcpy(h->d_window, win.data(), win.size() * sizeof(int16_t), cudaMemcpyHostToDevice), rxb200_power_destroy(h));
 	}
 	*out = h;
 	return RXB200_OK;
@@ -697,10 +704,11 @@ extern "C" void rxb200_power_destroy(rxb200_power *h)
 {
 	if (!h) { return; }
 	cudaSetDevice(h->device);
-	cudaStreamSynchronize(h->stream);
-	cudaFree(h->d_avg); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_db);
-	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-	cudaStreamDestroy(h->stream);
+	if (h->stream) { cudaStreamSynchronize(h->stream); }
+	cudaFree(h->d_avg); cudaFree(h->d_samples); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_db);
+	if (h->ev0) { cudaEventDestroy(h->ev0); }
+	if (h->ev1) { cudaEventDestroy(h->ev1); }
+	if (h->stream) { cudaStreamDestroy(h->stream); }
 	delete h;
 }
 
@@ -912,3 +920,246 @@ extern "C" int rxb200_power_reset(rxb200_power *h)
 
 extern "C" void *rxb200_power_stream(rxb200_power *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int rxb200_power_last_launches(rxb200_power *h) { return h ? h->launches : 0; }
+
+// ================================================================================ multi-GPU
+// Tuner hops are independent; rank r of n owns the contiguous hops [r*per, (r+1)*per), per = ceil(n_hops/n).
+// The report needs every row in hop order on the rank that prints (src/rtl_power.c:1047-1050): ONE all-gather of the
+// int64 rows (plus the tiny `samples` vector), in place on the accumulator array itself -- its zero padding rows make
+// n*per rows available on every rank, so nothing is allocated, zeroed or copied per report.
+struct rxb200_comm {
+	ncclComm_t comm;
+	int n_ranks, rank, device;
+};
+
+#define RXB_NCCL(api, call, cleanup)                                                                         \
+	do {                                                                                                     \
+		ncclResult_t r__ = (call);                                                                           \
+		if (r__ != ncclSuccess) {                                                                            \
+			set_error("%s failed: %s (%s:%d)", #call, (api)->GetErrorString(r__), __FILE__, __LINE__);       \
+			cleanup;                                                                                         \
+			return RXB200_ECUDA;                                                                             \
+		}                                                                                                    \
+	} while (0)
+
+extern "C" int rxb200_comm_unique_id(void *id128)
+{
+	if (!id128) { set_error("null argument"); return RXB200_EINVAL; }
+	const NcclApi *nc = nccl_api();
+	if (!nc) { return RXB200_EUNSUPPORTED; }
+	ncclUniqueId id;
+	RXB_NCCL(nc, nc->GetUniqueId(&id), (void)0);
+	memcpy(id128, &id, RXB200_UNIQUE_ID_BYTES);
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_comm_create(int n_ranks, int rank, const void *id128, int device, rxb200_comm **out)
+{
+	if (!out || !id128 || n_ranks < 1 || n_ranks > RXB_ROW_PAD || rank < 0 || rank >= n_ranks) {
+		set_error("bad communicator arguments (1 <= n_ranks <= %d)", RXB_ROW_PAD); return RXB200_EINVAL;
+	}
+	*out = nullptr;
+	const NcclApi *nc = nccl_api();
+	if (!nc) { return RXB200_EUNSUPPORTED; }
+	RXB_CUDA(cudaSetDevice(device));
+	rxb200_comm *c = new (std::nothrow) rxb200_comm();
+	if (!c) { return RXB200_ENOMEM; }
+	c->n_ranks = n_ranks; c->rank = rank; c->device = device; c->comm = nullptr;
+	ncclUniqueId id;
+	memcpy(&id, id128, RXB200_UNIQUE_ID_BYTES);
+	RXB_NCCL(nc, nc->CommInitRank(&c->comm, n_ranks, id, rank), delete c);
+	*out = c;
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_comm_create_all(int n_dev, const int *devices, rxb200_comm **out)
+{
+	if (!out || n_dev < 1 || n_dev > RXB_ROW_PAD) { set_error("bad communicator arguments (1 <= n_dev <= %d)", RXB_ROW_PAD); return RXB200_EINVAL; }
+	for (int i = 0; i < n_dev; i++) { out[i] = nullptr; }
+	const NcclApi *nc = nccl_api();
+	if (!nc) { return RXB200_EUNSUPPORTED; }
+	std::vector<ncclComm_t> comms((size_t)n_dev, nullptr);
+	std::vector<int> devs((size_t)n_dev);
+	for (int i = 0; i < n_dev; i++) { devs[i] = devices ? devices[i] : i; }
+	RXB_NCCL(nc, nc->CommInitAll(comms.data(), n_dev, devs.data()), (void)0);
+	for (int i = 0; i < n_dev; i++) {
+		rxb200_comm *c = new (std::nothrow) rxb200_comm();
+		if (!c) {
+			for (int j = 0; j < n_dev; j++) { if (j >= i) { nc->CommDestroy(comms[j]); } else { rxb200_comm_destroy(out[j]); out[j] = nullptr; } }
+			return RXB200_ENOMEM;
+		}
+		c->comm = comms[i]; c->n_ranks = n_dev; c->rank = i; c->device = devs[i];
+		out[i] = c;
+	}
+	return RXB200_OK;
+}
+
+extern "C" void rxb200_comm_destroy(rxb200_comm *c)
+{
+	if (!c) { return; }
+	const NcclApi *nc = nccl_api();
+	if (nc && c->comm) { cudaSetDevice(c->device); nc->CommDestroy(c->comm); }
+	delete c;
+}
+
+extern "C" int rxb200_comm_size(const rxb200_comm *c) { return c ? c->n_ranks : 0; }
+extern "C" int rxb200_comm_rank(const rxb200_comm *c) { return c ? c->rank : -1; }
+
+extern "C" int rxb200_power_shard(int n_hops, int n_ranks, int rank, int *hop_begin, int *hop_end)
+{
+	if (n_hops < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !hop_begin || !hop_end) { set_error("bad shard arguments"); return RXB200_EINVAL; }
+	const int per = (n_hops + n_ranks - 1) / n_ranks;
+	*hop_begin = rank * per < n_hops ? rank * per : n_hops;
+	*hop_end = (rank + 1) * per < n_hops ? (rank + 1) * per : n_hops;
+	return RXB200_OK;
+}
+
+// enqueue this rank's part of the collation on the handle's stream (inside a group when several handles of one
+// process take part)
+static int power_gather_enqueue(const NcclApi *nc, rxb200_power *h, rxb200_comm *c)
+{
+	const size_t N = (size_t)1 << h->p.bin_e;
+	const int per = (h->p.n_hops + c->n_ranks - 1) / c->n_ranks;
+	int hb = 0, he = 0;
+	rxb200_power_shard(h->p.n_hops, c->n_ranks, c->rank, &hb, &he);
+	RXB_CUDA(cudaSetDevice(h->device));
+	if (he > hb) {
+		RXB_CUDA(cudaMemcpyAsync(h->d_samples + hb, h->samples.data() + hb, (size_t)(he - hb) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	}
+	// in place: this rank's block already sits at rank*per rows from the start of the receive buffer
+	RXB_NCCL(nc, nc->AllGather(h->d_avg + (size_t)c->rank * per * N, h->d_avg, (size_t)per * N, ncclInt64, c->comm, h->stream), (void)0);
+	RXB_NCCL(nc, nc->AllGather(h->d_samples + (size_t)c->rank * per, h->d_samples, (size_t)per, ncclInt32, c->comm, h->stream), (void)0);
+	return RXB200_OK;
+}
+
+static int power_gather_finish(rxb200_power *h, int sync)
+{
+	RXB_CUDA(cudaSetDevice(h->device));
+	// the host mirror of `samples` follows the gathered copy (pinned-less D2H of n_hops ints)
+	RXB_CUDA(cudaMemcpyAsync(h->samples.data(), h->d_samples, (size_t)h->p.n_hops * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	if (sync) { RXB_CUDA(cudaStreamSynchronize(h->stream)); }
+	return RXB200_OK;
+}
+
+static int power_gather_check(const rxb200_power *h, const rxb200_comm *c)
+{
+	if (!h || !c) { set_error("null argument"); return RXB200_EINVAL; }
+	if (c->device != h->device) { set_error("communicator is on device %d, the handle on %d", c->device, h->device); return RXB200_EINVAL; }
+	const int per = (h->p.n_hops + c->n_ranks - 1) / c->n_ranks;
+	if ((long long)per * c->n_ranks > (long long)h->p.n_hops + RXB_ROW_PAD) { set_error("too many ranks for the row padding"); return RXB200_EINVAL; }
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_power_gather(rxb200_power *h, rxb200_comm *c, int sync)
+{
+	int rc = power_gather_check(h, c);
+	if (rc != RXB200_OK) { return rc; }
+	if (c->n_ranks == 1) { if (sync) { RXB_CUDA(cudaSetDevice(h->device)); RXB_CUDA(cudaStreamSynchronize(h->stream)); } return RXB200_OK; }
+	const NcclApi *nc = nccl_api();
+	if (!nc) { return RXB200_EUNSUPPORTED; }
+	RXB_NCCL(nc, nc->GroupStart(), (void)0);
+	rc = power_gather_enqueue(nc, h, c);
+	RXB_NCCL(nc, nc->GroupEnd(), (void)0);
+	if (rc != RXB200_OK) { return rc; }
+	return power_gather_finish(h, sync);
+}
+
+// ---- all ranks in ONE process (the C drop-in shell): n_dev handles with identical parameters, one per GPU
+struct rxb200_power_group {
+	int n_dev;
+	std::vector<rxb200_power *> h;
+	std::vector<rxb200_comm *> c;
+};
+
+extern "C" void rxb200_power_group_destroy(rxb200_power_group *g)
+{
+	if (!g) { return; }
+	for (auto *c : g->c) { rxb200_comm_destroy(c); }
+	for (auto *h : g->h) { rxb200_power_destroy(h); }
+	delete g;
+}
+
+extern "C" int rxb200_power_group_create(const rxb200_power_params *params, const int *window_coefs, const int16_t *sinewave,
+                                         int n_dev, const int *devices, rxb200_power_group **out)
+{
+	if (!out || n_dev < 1 || n_dev > RXB_ROW_PAD) { set_error("bad group arguments (1 <= n_dev <= %d)", RXB_ROW_PAD); return RXB200_EINVAL; }
+	*out = nullptr;
+	rxb200_power_group *g = new (std::nothrow) rxb200_power_group();
+	if (!g) { return RXB200_ENOMEM; }
+	g->n_dev = n_dev;
+	g->h.assign((size_t)n_dev, nullptr);
+	g->c.assign((size_t)n_dev, nullptr);
+	for (int i = 0; i < n_dev; i++) {
+		int rc = rxb200_power_create(params, window_coefs, sinewave, devices ? devices[i] : i, &g->h[(size_t)i]);
+		if (rc != RXB200_OK) { rxb200_power_group_destroy(g); return rc; }
+	}
+	if (n_dev > 1) {
+		int rc = rxb200_comm_create_all(n_dev, devices, g->c.data());
+		if (rc != RXB200_OK) { rxb200_power_group_destroy(g); return rc; }
+	}
+	*out = g;
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_power_group_size(const rxb200_power_group *g) { return g ? g->n_dev : 0; }
+extern "C" rxb200_power *rxb200_power_group_member(rxb200_power_group *g, int i) { return (g && i >= 0 && i < g->n_dev) ? g->h[(size_t)i] : nullptr; }
+
+// hop_bufs as in rxb200_power_accumulate (HOST pointer, [n_pass][hop_end-hop_begin][buf_len]); every member takes the
+// hops of the range it owns.  Copies and kernels of the members overlap (one stream per GPU), the call returns when
+// all are done.
+extern "C" int rxb200_power_group_accumulate(rxb200_power_group *g, const int16_t *hop_bufs, int n_pass, int hop_begin, int hop_end)
+{
+	if (!g || !hop_bufs) { set_error("null argument"); return RXB200_EINVAL; }
+	const rxb200_power_params &p = g->h[0]->p;
+	if (n_pass < 0 || hop_begin < 0 || hop_end > p.n_hops || hop_begin >= hop_end) { set_error("bad hop range"); return RXB200_EINVAL; }
+	const int nh = hop_end - hop_begin;
+	for (int i = 0; i < g->n_dev; i++) {
+		int hb, he;
+		rxb200_power_shard(p.n_hops, g->n_dev, i, &hb, &he);
+		const int b = hb > hop_begin ? hb : hop_begin, e = he < hop_end ? he : hop_end;
+		if (b >= e) { continue; }
+		rxb200_power *h = g->h[(size_t)i];
+		RXB_CUDA(cudaSetDevice(h->device));
+		const size_t elems = (size_t)n_pass * (size_t)(e - b) * (size_t)p.buf_len;
+		if (elems > h->d_in_cap) {
+			cudaFree(h->d_in); h->d_in = nullptr; h->d_in_cap = 0;
+			RXB_CUDA(cudaMalloc(&h->d_in, elems * sizeof(int16_t)));
+			h->d_in_cap = elems;
+		}
+		// the member's hops of every pass, packed [n_pass][e-b][buf_len] on its device
+		RXB_CUDA(cudaMemcpy2DAsync(h->d_in, (size_t)(e - b) * p.buf_len * sizeof(int16_t),
+		                           hop_bufs + (size_t)(b - hop_begin) * p.buf_len, (size_t)nh * p.buf_len * sizeof(int16_t),
+		                           (size_t)(e - b) * p.buf_len * sizeof(int16_t), (size_t)n_pass, cudaMemcpyHostToDevice, h->stream));
+		int rc = rxb200_power_accumulate_device(h, h->d_in, n_pass, b, e, 0);
+		if (rc != RXB200_OK) { return rc; }
+	}
+	for (int i = 0; i < g->n_dev; i++) {
+		RXB_CUDA(cudaSetDevice(g->h[(size_t)i]->device));
+		RXB_CUDA(cudaStreamSynchronize(g->h[(size_t)i]->stream));
+	}
+	return RXB200_OK;
+}
+
+// the collation: after it EVERY member holds all rows and samples, so member 0 can be read or reported as if it had
+// processed every hop itself
+extern "C" int rxb200_power_group_gather(rxb200_power_group *g)
+{
+	if (!g) { set_error("null argument"); return RXB200_EINVAL; }
+	if (g->n_dev == 1) { return RXB200_OK; }
+	const NcclApi *nc = nccl_api();
+	if (!nc) { return RXB200_EUNSUPPORTED; }
+	for (int i = 0; i < g->n_dev; i++) { int rc = power_gather_check(g->h[(size_t)i], g->c[(size_t)i]); if (rc != RXB200_OK) { return rc; } }
+	RXB_NCCL(nc, nc->GroupStart(), (void)0);
+	int rc = RXB200_OK;
+	for (int i = 0; i < g->n_dev && rc == RXB200_OK; i++) { rc = power_gather_enqueue(nc, g->h[(size_t)i], g->c[(size_t)i]); }
+	RXB_NCCL(nc, nc->GroupEnd(), (void)0);
+	if (rc != RXB200_OK) { return rc; }
+	for (int i = 0; i < g->n_dev; i++) { rc = power_gather_finish(g->h[(size_t)i], 1); if (rc != RXB200_OK) { return rc; } }
+	return RXB200_OK;
+}
+
+extern "C" int rxb200_power_group_reset(rxb200_power_group *g)
+{
+	if (!g) { return RXB200_EINVAL; }
+	for (auto *h : g->h) { int rc = rxb200_power_reset(h); if (rc != RXB200_OK) { return rc; } }
+	return RXB200_OK;
+}

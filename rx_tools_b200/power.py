@@ -147,6 +147,11 @@ class PowerScanner:
         _lib.check(_lib.lib().rxb200_power_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def gather(self, comm: "Comm", sync: bool = True) -> None:
+        """The collation before the report (src/rtl_power.c:1047-1050 walks every hop): ONE in-place NCCL all-gather of
+        the accumulator rows inside the library; afterwards read()/read_db() see every rank's hops."""
+        _lib.check(_lib.lib().rxb200_power_gather(self._h, comm._c, 1 if sync else 0))
+
     @property
     def device_avg_ptr(self) -> int:
         return int(_lib.lib().rxb200_power_device_avg(self._h) or 0)
@@ -172,3 +177,77 @@ def csv_rows(plan: Plan, avg: np.ndarray, samples: np.ndarray, tstr: str = "2026
                                                           int(samples[i]), buf, len(buf)))
         lines.append(tstr + ", " + buf.raw[:r].decode())
     return "".join(lines)
+
+
+def shard(n_hops: int, n_ranks: int, rank: int):
+    """Contiguous hop range [begin, end) of `rank` (rxb200_power_shard)."""
+    b, e = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.lib().rxb200_power_shard(n_hops, n_ranks, rank, C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+class Comm:
+    """One rank's NCCL communicator, owned by librxb200 (include/rxb200.h: rxb200_comm_*)."""
+
+    def __init__(self, n_ranks: int, rank: int, unique_id: bytes, device: int):
+        assert len(unique_id) == 128
+        self._c = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        _lib.check(_lib.lib().rxb200_comm_create(n_ranks, rank, buf, device, C.byref(self._c)))
+        self.n_ranks, self.rank = n_ranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.lib().rxb200_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self) -> None:
+        if getattr(self, "_c", None) is not None and self._c:
+            _lib.lib().rxb200_comm_destroy(self._c)
+            self._c = None
+
+    __del__ = close
+
+
+class PowerGroup:
+    """All ranks in one process: n_dev GPUs, hops sharded, one all-gather before the report (what the drop-in
+    rx_power_b200 shell uses when RXB200_GPUS > 1)."""
+
+    def __init__(self, plan: Plan, window: Sequence[int] | str = "rectangle", n_dev: int = 1):
+        self.plan = plan
+        n = 1 << plan.bin_e
+        self.window = window_table(window, n) if isinstance(window, str) else np.ascontiguousarray(window, np.int32)
+        self._g = C.c_void_p()
+        pc = plan.to_c()
+        _lib.check(_lib.lib().rxb200_power_group_create(C.byref(pc), self.window.ctypes.data_as(C.POINTER(C.c_int)), None,
+                                                        n_dev, None, C.byref(self._g)))
+        self.n_dev = n_dev
+
+    def close(self) -> None:
+        if getattr(self, "_g", None) is not None and self._g:
+            _lib.lib().rxb200_power_group_destroy(self._g)
+            self._g = None
+
+    __del__ = close
+
+    def scanner(self, hop_bufs: np.ndarray, n_pass: int, hop_begin: int = 0, hop_end: Optional[int] = None) -> None:
+        hop_end = self.plan.n_hops if hop_end is None else hop_end
+        hb = np.ascontiguousarray(hop_bufs, dtype=np.int16).reshape(-1)
+        assert hb.size == n_pass * (hop_end - hop_begin) * self.plan.buf_len
+        _lib.check(_lib.lib().rxb200_power_group_accumulate(self._g, hb.ctypes.data, n_pass, hop_begin, hop_end))
+
+    def gather(self) -> None:
+        _lib.check(_lib.lib().rxb200_power_group_gather(self._g))
+
+    def read(self, member: int = 0):
+        n = 1 << self.plan.bin_e
+        avg = np.zeros((self.plan.n_hops, n), dtype=np.int64)
+        samples = np.zeros(self.plan.n_hops, dtype=np.int32)
+        h = _lib.lib().rxb200_power_group_member(self._g, member)
+        _lib.check(_lib.lib().rxb200_power_read(h, avg.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                samples.ctypes.data_as(C.POINTER(C.c_int))))
+        return avg, samples
+
+    def reset(self) -> None:
+        _lib.check(_lib.lib().rxb200_power_group_reset(self._g))

@@ -21,8 +21,19 @@ def unit_range(rank: int, world: int, n_units: int) -> Tuple[int, int]:
     return min(rank * per, n_units), min((rank + 1) * per, n_units)
 
 
+def make_comm(rank: int, world: int, device: int, group=None):
+    """librxb200's own NCCL communicator for this rank (rx_tools_b200.power.Comm).  torch.distributed only carries
+    the 128-byte unique id from rank 0 to the others -- plumbing; the all-gather itself runs inside the library."""
+    import torch.distributed as dist
+    from . import power
+    box = [power.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return power.Comm(world, rank, box[0], device)
+
+
 def gather_rows(local_rows, n_units: int, row_len: int, world: int, group=None):
-    """all_gather of equal-sized row blocks; local_rows: int64 tensor [(end-begin) * row_len] on the rank's
+    """Host-logic stand-in of rxb200_power_gather for the CPU (gloo) tests: the same partition, padding and order.
+    all_gather of equal-sized row blocks; local_rows: int64 tensor [(end-begin) * row_len] on the rank's
     device (cuda with nccl, cpu with gloo).  Returns the [n_units, row_len] tensor in unit order."""
     import torch
     import torch.distributed as dist

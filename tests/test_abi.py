@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f"librxb200.so does not export {s}"
     assert sorted(_lib.SYMBOLS) == syms
-    assert L.rxb200_abi_version() == 2
+    assert L.rxb200_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():

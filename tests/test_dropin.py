@@ -138,3 +138,27 @@ def test_rx_power_csv(tmp_path, port, freq, crop, win):
     avg, smp = port.power_scan(pp, power.window_table(win, 1 << plan.bin_e), hb, n_pass, plan.n_hops)
     want = power.csv_rows(plan, avg, smp, "2026-01-01, 00:00:00")
     assert got == want
+
+
+def test_rx_power_csv_on_two_gpus(tmp_path, port):
+    """RXB200_GPUS=2: hops sharded over two GPUs, one NCCL all-gather before the report; the CSV bytes are those of
+    the single-GPU run (and of the oracle)."""
+    from rx_tools_b200 import _lib
+    if int(_lib.lib().rxb200_device_count()) < 2:
+        pytest.skip("needs 2 GPUs")
+    freq, crop, win, n_pass = "24M:60M:1k", "28.5%", "hamming", 2
+    plan = power.plan_range(freq, 0.285)
+    hb = synth.power_hops(n_pass, plan.n_hops, plan.buf_len, seed=72)
+    cap = tmp_path / "cap.cs16"
+    _power_capture(plan, hb, n_pass).tofile(cap)
+    outs = []
+    for g in ("1", "2"):
+        out = tmp_path / f"out{g}.csv"
+        _run([RX_POWER, "-f", freq, "-c", crop, "-w", win, "-i", "1h", "-d", f"driver=file,path={cap}", str(out)],
+             env={"RXB200_MAX_SWEEPS": str(n_pass), "RXB200_FIXED_TIME": "2026-01-01, 00:00:00", "RXB200_GPUS": g})
+        outs.append(open(out).read())
+    pp = oracle.PowerParams(bin_e=plan.bin_e, buf_len=plan.buf_len)
+    avg, smp = port.power_scan(pp, power.window_table(win, 1 << plan.bin_e), hb, n_pass, plan.n_hops)
+    want = power.csv_rows(plan, avg, smp, "2026-01-01, 00:00:00")
+    assert outs[0] == want
+    assert outs[1] == want
