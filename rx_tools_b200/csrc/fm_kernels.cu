@@ -406,9 +406,11 @@ __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int
 	if (!c.resample) { return m; }
 	return ((long long)phase0 + m * (long long)c.slow) / (long long)c.fast;
 }
-// shared PCM buffer: 4 bytes of padding per 128 entries so that neither the front-end stores
-// (thread stride ~ Sf/D entries) nor the back-end loads (lane stride = piece) pile on one bank
-__device__ __forceinline__ int pcm_phys(int rel) { return rel + 2 * (rel >> 7); }
+// shared PCM buffer: 16 bytes of padding per 128 entries so that neither the front-end stores
+// (thread stride ~ Sf/D entries) nor the back-end loads (lane stride = piece) pile on one bank; 16 keeps
+// the row front end's 8/16-byte vector stores aligned (fm_rows.cuh)
+#define PCM_PAD 8
+__device__ __forceinline__ int pcm_phys(int rel) { return rel + PCM_PAD * (rel >> 7); }
 
 // Compile-time specialisation of the flags that sit in the per-sample path.  SPEC 0: everything is a
 // (warp-uniform) run-time branch.  SPEC 1: the wbfm shape — FM discriminator with fast_atan2, fs/4
@@ -1532,7 +1534,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		n_extra = direct_out ? 0 : (margin_dec * Dpcm + halo + sf - 1) / sf;
 		ppt = sf / Dpcm + 2;
 		pcm_cap = direct_out ? 8 : (long long)T * ppt + 64;
-		pcm_cap += 2 * (pcm_cap >> 7) + 8;
+		pcm_cap += PCM_PAD * (pcm_cap >> 7) + 16;
 		smem = (size_t)pcm_cap * sizeof(int16_t);
 		if ((long long)smem > h->smem_optin || n_extra > T / 2) { return false; }
 		n_own = T - n_extra;
