@@ -39,7 +39,7 @@ class FmDerivedC(C.Structure):
 
 
 class FmStatsC(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("launches", "segments", "fixup_segments", "segment_len", "warmup_len")]
+    _fields_ = [(n, C.c_int) for n in ("launches", "segments", "fixup_segments", "segment_len", "warmup_len", "kernel_kind")]
 
 
 class PowerParamsC(C.Structure):

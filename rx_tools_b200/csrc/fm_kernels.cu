@@ -70,6 +70,8 @@ struct FmCall {
 	int pcm_cap;              // int16 entries of the shared PCM buffer
 	int direct_out;           // 1: no serial stage, the front end stores the output itself
 	int be_lanes;             // threads of the CTA that run the back end (multiple of 32)
+	int fe_threads, fe_warps; // split kernel: threads / warps of the CTA that run the front end
+	int xs_words;             // split kernel, row front end: words of a warp's exchange area
 	int state_words;
 	const uint32_t *carry_in; // [n_ch][state_words]
 	uint32_t *carry_out;      // [n_ch][state_words]
@@ -1113,6 +1115,65 @@ __global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3
 	}
 }
 
+#include "fm_rows.cuh"
+
+// ---- split kernel: front end and back end of a CTA work on DIFFERENT items.
+// In fm_fused_kernel every warp runs the front end of an item and then parks at a barrier while the first warps
+// run the serial stages (22 % of the warp time on the wbfm shape, 62 % with de-emphasis at 2.4 Msps).  Here the
+// CTA's last `be_lanes` threads do nothing but the back end: the front-end warps fill one of two PCM buffers and
+// move on to the next item; the hand-off is a pair of mbarriers per buffer (full: front end -> back end, empty:
+// back end -> front end), item tickets travel through shared memory.  An item still only ever waits for OLDER
+// items (look-back in back_item), every CTA of the grid is resident, so the oldest unfinished item always advances.
+//   FE 0: per-thread segments (front_item)   FE 1: warp rows with the droop FIR (fm_rows.cuh)   FE 2: rows, no FIR
+#define BAR_FE 2
+#define SPLIT_BE_MAX 128
+template <int P, int SPEC, int FE, int TMAX, int MINB>
+__global__ void __launch_bounds__(TMAX, MINB) fm_split_kernel(const FmDev c, const FmCall k)
+{
+	extern __shared__ __align__(16) int16_t pcm_s[];       // [2][pcm_cap] PCM buffers, then the row exchange areas
+	__shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+	__shared__ int s_ticket[2];
+	__shared__ int s_avg[SPLIT_BE_MAX], s_mrun[SPLIT_BE_MAX], s_start[SPLIT_BE_MAX];
+	__shared__ unsigned char s_ok[SPLIT_BE_MAX];
+	const int tid = threadIdx.x;
+	const int n_fe = k.fe_threads;
+	if (tid == 0) {
+		mbar_init(&s_full[0], n_fe); mbar_init(&s_full[1], n_fe);
+		mbar_init(&s_empty[0], k.be_lanes); mbar_init(&s_empty[1], k.be_lanes);
+	}
+	__syncthreads();
+	const int total_work = k.n_ch * k.n_cta;
+	if (tid < n_fe) {
+		for (int i = 0;; i++) {
+			const int b = i & 1;
+			if (i >= 2) { mbar_wait(&s_empty[b], (uint32_t)(((i >> 1) - 1) & 1)); }   // the back end is done with item i-2
+			if (tid == 0) { s_ticket[b] = atomicAdd(k.ticket, 1); }
+			bar_sync(BAR_FE, n_fe);
+			const int work = s_ticket[b];
+			if (work >= total_work) { mbar_arrive(&s_full[b]); break; }                // the back end sees the sentinel
+			const Item it = make_item(c, k, work);
+			int16_t *buf = pcm_s + (size_t)b * k.pcm_cap;
+			if constexpr (FE == 0) { front_item<P, SPEC>(c, k, it, tid, buf); }
+			else {
+				uint32_t *xs = reinterpret_cast<uint32_t *>(pcm_s + 2 * (size_t)k.pcm_cap) + (size_t)(tid >> 5) * k.xs_words;
+				front_rows<P, FE == 1>(c, k, it, tid >> 5, tid & 31, buf, xs);
+			}
+			mbar_arrive(&s_full[b]);
+		}
+	} else {
+		const int q = tid - n_fe;
+		for (int i = 0;; i++) {
+			const int b = i & 1;
+			mbar_wait(&s_full[b], (uint32_t)((i >> 1) & 1));
+			const int work = s_ticket[b];
+			if (work >= total_work) { break; }
+			const Item it = make_item(c, k, work);
+			back_item<SPEC>(c, k, it, work, q, k.be_lanes, pcm_s + (size_t)b * k.pcm_cap, s_avg, s_mrun, s_ok, s_start);
+			mbar_arrive(&s_empty[b]);
+		}
+	}
+}
+
 // ---- per-chunk reduction pre-passes: the scalar recurrences across chunks (one thread per channel)
 
 // dc_block_raw_filter (src/rtl_fm.c:699-721): sums of the SCALED I and Q of every chunk
@@ -1235,6 +1296,25 @@ static fm_kernel_fn pick_kernel_p(int P, int threads)
 #endif
 }
 
+// the split kernel with the row front end exists for the wbfm shape with 1..3 packed passes
+#define ROWS_FE_WARPS 8
+#define ROWS_TMAX (ROWS_FE_WARPS * 32 + 32)
+#define ROWS_MINB 2
+static fm_kernel_fn pick_rows_kernel(int P, int fir_on)
+{
+#ifdef RXB_QUICK
+	return (P == 3 && fir_on) ? fm_split_kernel<3, 1, 1, ROWS_TMAX, ROWS_MINB> : nullptr;
+#else
+	switch (P) {
+	case 1: return fir_on ? fm_split_kernel<1, 1, 1, ROWS_TMAX, ROWS_MINB> : fm_split_kernel<1, 1, 2, ROWS_TMAX, ROWS_MINB>;
+	case 2: return fir_on ? fm_split_kernel<2, 1, 1, ROWS_TMAX, ROWS_MINB> : fm_split_kernel<2, 1, 2, ROWS_TMAX, ROWS_MINB>;
+	case 3: return fir_on ? fm_split_kernel<3, 1, 1, ROWS_TMAX, ROWS_MINB> : fm_split_kernel<3, 1, 2, ROWS_TMAX, ROWS_MINB>;
+	default: return nullptr;
+	}
+#endif
+}
+static int rows_xs_words(int P) { return P == 1 ? RowSmem<1>::WORDS : (P == 2 ? RowSmem<2>::WORDS : RowSmem<3>::WORDS); }
+
 static fm_kernel_fn pick_kernel(int P, int spec, int threads)
 {
 	if (spec == 1 && P <= 4) { return pick_kernel_p<1>(P, threads); }
@@ -1282,9 +1362,13 @@ struct rxb200_fm {
 	int tune_seg, tune_warm;
 	rxb200_fm_stats stats;
 	fm_kernel_fn kern;
+	fm_kernel_fn kern_rows;        // split kernel with the row front end (null: shape not covered)
+	int spec;
+	int last_rows;                 // 1: the last process call ran kern_rows
+	int rows_fe_warps, rows_be_lanes;
 	int threads;                   // CTA width of kern
 	int wide;                      // all-scalar fifth_order passes (raw DC block on)
-	int smem_optin;
+	int smem_optin, smem_per_sm, smem_reserved;
 	// per-chunk reduction stages
 	long long *d_sums; int *d_rdc, *d_sqz, *d_adc, *d_lens, *d_levels; size_t chunk_cap; int level_chunks;
 	std::vector<int> *h_lens;
@@ -1368,12 +1452,23 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		                                 !params->offset_tuning && serial && plain) ? 1 : 0);
 		h->threads = fm_cta_threads(params->downsample_passes, params->downsample);
 		h->kern = pick_kernel(params->downsample_passes, spec, h->threads);
+		h->spec = spec;
+		const int fir_on = (params->downsample_passes > 0 && params->comp_fir_size == 9) ? 1 : 0;
+		h->kern_rows = (spec == 1 && !getenv("RXB200_FM_NOROWS")) ? pick_rows_kernel(params->downsample_passes, fir_on) : nullptr;
+		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = 32;
+		{
+			// A/B knobs, read once at create: back-end lanes (32 | 64 ...) of the split kernel
+			const char *e = getenv("RXB200_FM_ROWS_BE");
+			if (e && atoi(e) >= 32 && atoi(e) <= SPLIT_BE_MAX && atoi(e) % 32 == 0 && ROWS_FE_WARPS * 32 + atoi(e) <= ROWS_TMAX) { h->rows_be_lanes = atoi(e); }
+		}
 	}
 	if (!h->kern) { set_error("no kernel for downsample_passes %d in this build", params->downsample_passes); delete h->h_lens; delete h; return RXB200_EUNSUPPORTED; }
 	cudaDeviceProp prop;
 	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
 	h->n_sm = prop.multiProcessorCount;
 	h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+	h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+	h->smem_reserved = (int)prop.reservedSharedMemPerBlock;
 	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	RXB_CUDA(cudaEventCreate(&h->ev0));
 	RXB_CUDA(cudaEventCreate(&h->ev1));
@@ -1497,9 +1592,105 @@ static int fm_check_shape(const rxb200_fm *h, size_t n_int16, size_t chunk_int16
 
 static long long round_up_ll(long long v, long long g) { return ((v + g - 1) / g) * g; }
 
+// ---- launch of the split kernel with the row front end (fm_rows.cuh).  Geometry in ROWS of ROW_LEN input samples:
+// an item owns `rows_own` rows, its warps also produce the `rows_margin` rows before them (the back end's replay
+// window); the two PCM buffers and the warps' exchange areas share the CTA's dynamic shared memory.
+static bool fm_rows_shape_ok(const rxb200_fm *h, size_t n_int16, size_t chunk_int16)
+{
+	if (!h->kern_rows) { return false; }
+	const size_t n = n_int16 / 2, chunk = chunk_int16 / 2;
+	return chunk % ROW_LEN == 0 && n % ROW_LEN == 0 && n >= 16 * (size_t)ROW_LEN;
+}
+
+static int fm_launch_rows(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t chunk_int16, int16_t *d_out, size_t out_stride)
+{
+	const rxb200_fm_params &p = h->p;
+	const FmDev &dv = h->dev;
+	const long long n = (long long)(n_int16 / 2);
+	const int P = p.downsample_passes;
+	const long long rows_total = n / ROW_LEN;
+	const long long row_pcm = ROW_LEN >> P;                 // PCM samples per row
+	long long W_dec = 0;
+	if (dv.deemph) { W_dec = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
+	const long long margin_dec = W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
+	const long long rows_margin = (margin_dec + row_pcm - 1) / row_pcm;
+	const int fe_warps = h->rows_fe_warps, be_lanes = h->rows_be_lanes;
+	const int threads = fe_warps * 32 + be_lanes;
+	const int xs_words = rows_xs_words(P);
+	const size_t xs_bytes = (size_t)fe_warps * xs_words * sizeof(uint32_t);
+	cudaFuncAttributes fa;
+	RXB_CUDA(cudaFuncGetAttributes(&fa, h->kern_rows));
+	// shared memory of one CTA when ROWS_MINB of them share an SM
+	long long dyn_max = (long long)h->smem_per_sm / ROWS_MINB - (long long)h->smem_reserved - (long long)fa.sharedSizeBytes;
+	if (dyn_max > h->smem_optin - (long long)fa.sharedSizeBytes) { dyn_max = h->smem_optin - (long long)fa.sharedSizeBytes; }
+	auto cap_for = [&](long long rows_item) -> long long {
+		long long e = rows_item * row_pcm + 8;              // one entry of slack is read past the last sample (back_outputs)
+		e += PCM_PAD * (e >> 7) + 16;
+		return (e + 7) & ~7LL;                               // the second buffer and the exchange areas stay 16-byte aligned
+	};
+	long long rows_item = ((dyn_max - (long long)xs_bytes) / 2 / (long long)sizeof(int16_t)) / (row_pcm + (row_pcm * PCM_PAD) / 128 + 1);
+	while (rows_item > rows_margin + 1 && 2 * cap_for(rows_item) * (long long)sizeof(int16_t) + (long long)xs_bytes > dyn_max) { rows_item--; }
+	long long rows_own = rows_item - rows_margin;
+	if (rows_own < 1) { set_error("the back-end replay (%lld PCM samples) does not fit the split kernel's PCM buffers", margin_dec); return RXB200_EUNSUPPORTED; }
+	if (h->tune_seg > 0) {
+		long long t = h->tune_seg / ROW_LEN;
+		if (t < 1) { t = 1; }
+		if (t < rows_own) { rows_own = t; }
+	} else {
+		// whole waves of the resident CTAs: a slightly shorter item beats a ragged last wave
+		const long long slots = (long long)h->n_sm * ROWS_MINB;
+		const long long items = (rows_total * h->n_channels + rows_own - 1) / rows_own;
+		if (items > slots) {
+			const long long waves = (items + slots - 1) / slots;
+			const long long t = (rows_total * h->n_channels + waves * slots - 1) / (waves * slots);
+			if (t >= 1 && t < rows_own && t * 10 >= rows_own * 6) { rows_own = t; }
+		}
+	}
+	if (rows_own > rows_total) { rows_own = rows_total; }
+	rows_item = rows_own + rows_margin;
+	const long long pcm_cap = cap_for(rows_item);
+	const size_t smem = 2 * (size_t)pcm_cap * sizeof(int16_t) + xs_bytes;
+	const long long n_cta = (rows_total + rows_own - 1) / rows_own;
+	RXB_CUDA(cudaFuncSetAttribute(h->kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern_rows, threads, smem));
+	if (per_sm < 1) { set_error("split kernel does not fit an SM (%zu bytes of shared memory, %d threads)", smem, threads); return RXB200_EUNSUPPORTED; }
+	const size_t total_work = (size_t)n_cta * h->n_channels;
+	const size_t need_sync = 4 + 4 * total_work;
+	if (need_sync > h->sync_cap) {
+		cudaFree(h->d_sync); h->d_sync = nullptr; h->sync_cap = 0;
+		RXB_CUDA(cudaMalloc(&h->d_sync, need_sync * sizeof(int)));
+		h->sync_cap = need_sync;
+	}
+	FmCall k;
+	memset(&k, 0, sizeof k);
+	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
+	k.n_ch = h->n_channels; k.Sf = ROW_LEN; k.halo = 0; k.n_extra = (int)rows_margin; k.n_own = (int)rows_own;
+	k.n_cta = (int)n_cta; k.W_dec = (int)W_dec; k.pcm_cap = (int)pcm_cap; k.direct_out = 0;
+	k.be_lanes = be_lanes; k.fe_warps = fe_warps; k.fe_threads = fe_warps * 32; k.xs_words = xs_words;
+	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
+	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
+	k.n_chunks = (int)((n + k.chunk - 1) / k.chunk);
+	k.reduce_mode = 0; k.one = 1;
+	size_t blocks = (size_t)h->n_sm * per_sm;
+	if (blocks > total_work) { blocks = total_work; }
+	RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
+	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
+	h->kern_rows<<<(unsigned)blocks, threads, smem, h->stream>>>(dv, k);
+	RXB_CUDA(cudaGetLastError());
+	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
+	h->cur ^= 1;
+	h->last_rows = 1;
+	h->stats.launches = 1; h->stats.segments = (int)(total_work * fe_warps); h->stats.segment_len = (int)(rows_own * ROW_LEN);
+	h->stats.warmup_len = (int)(W_dec << P); h->stats.fixup_segments = -1; h->stats.kernel_kind = 1;
+	return RXB200_OK;
+}
+
 static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t chunk_int16, int16_t *d_out,
                      size_t out_stride)
 {
+	if (fm_rows_shape_ok(h, n_int16, chunk_int16)) { return fm_launch_rows(h, d_in, n_int16, chunk_int16, d_out, out_stride); }
+	h->last_rows = 0;
 	const rxb200_fm_params &p = h->p;
 	const FmDev &dv = h->dev;
 	const long long n = (long long)(n_int16 / 2);
@@ -1689,7 +1880,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	}
 	h->cur ^= 1;
 	h->stats.launches = launches; h->stats.segments = (int)(total_work * T); h->stats.segment_len = (int)Sf;
-	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1;
+	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1; h->stats.kernel_kind = 0;
 	return RXB200_OK;
 }
 

@@ -1,0 +1,258 @@
+// fm_rows.cuh — the "row" front end of the split rx_fm kernel (included by fm_kernels.cu inside namespace rxb).
+//
+// The segment front end (front_item) gives every THREAD its own contiguous segment: the price is a halo of
+// 16 decimated samples replayed per thread (16 % of the work at 824-sample segments) and one private 32-byte
+// load stream per thread.  Here a WARP owns a contiguous stretch of the stream and walks it in rows of
+// ROW_LEN = 1024 input samples; lane l takes samples [32 l, 32 l + 32) of the row.  The finite-memory chain
+//   scale (src/rtl_fm.c:846) -> rotate16_90 (:309) -> fifth_order x P (:411) -> generic_fir (:442) -> fm_demod (:584)
+// is evaluated level by level on the lane's block; what a level needs from BEFORE the block (the last five
+// inputs of that level, nine for the droop FIR, one for the discriminator) is the neighbouring lane's tail,
+// handed over through a 1.8 KB per-warp exchange area in shared memory (lane 0 receives lane 31's tail of
+// the previous row).  Nothing is replayed per lane; a warp replays ONE row before its stretch (the chain's
+// memory is 128 samples) and the loads are whole 128-byte lines.
+//
+// Per-chunk semantics stay literal: a chunk is a whole number of rows, so only lane 0 of a
+// chunk's first row sees the boundary -- there every pass drops its pending odd sample (the history is taken
+// one sample older) and the first discriminator output goes through atan2.
+#pragma once
+
+#define ROW_LANE 32                    // input samples per lane per row
+#define ROW_LEN (32 * ROW_LANE)        // input samples per warp row
+#define ROW_PF 3                       // L2 prefetch distance in rows
+
+template <int P>
+struct RowSmem {                       // word offsets inside a warp's exchange area
+	static constexpr int NV = ROW_LANE >> P;                 // decimated samples per lane per row
+	static constexpr int SLOT = 0;                           // [32][8]: slot l+1 = tail of lane l (six words used)
+	static constexpr int CARRY = 256;                        // [3 levels][2 parities][8]: lane 31's tail of a row
+	static constexpr int VRING = CARRY + 48;                 // [12 + 32 NV]: droop FIR inputs, 12 of the previous row first
+	static constexpr int FPRE = VRING + 12 + 32 * NV;        // [2 parities]: last FIR output of a row (raw I/Q pair)
+	static constexpr int WORDS = FPRE + 4;
+};
+
+__device__ __forceinline__ void ldg256_row(const int16_t *p, uint32_t *v, uint32_t dep)
+{
+	asm volatile("ld.global.nc.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+	             : "l"(p), "r"(dep));
+}
+
+// a lane's 32 samples of one row (128 bytes, one line); `dep` only orders the loads behind its producer
+__device__ __forceinline__ void row_load(const int16_t *in_row, int lane, uint32_t (&v)[ROW_LANE], uint32_t dep)
+{
+	const int16_t *p = in_row + 2 * ROW_LANE * lane;
+#pragma unroll
+	for (int q = 0; q < ROW_LANE / 8; q++) { ldg256_row(p + 16 * q, &v[8 * q], dep); }
+}
+
+// hand the level's tail (its last six inputs, oldest first) to the next lane and fetch the five inputs before this
+// lane's block.  cs0: lane 0 of a chunk's first row -- the pass forgot its pending odd sample, the history is one older.
+__device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carry_r, int lane, bool cs0,
+                                             uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
+                                             uint32_t (&h)[5])
+{
+	__syncwarp();                          // the slots' previous readers are done
+	uint32_t *wr = (lane == 31) ? xs + carry_w : xs + 8 * (lane + 1);
+	*reinterpret_cast<uint4 *>(wr) = make_uint4(t0, t1, t2, t3);
+	*reinterpret_cast<uint2 *>(wr + 4) = make_uint2(t4, t5);
+	__syncwarp();
+	const uint32_t *rd = (lane == 0) ? xs + carry_r : xs + 8 * lane;
+	const uint4 a = *reinterpret_cast<const uint4 *>(rd);
+	const uint2 b = *reinterpret_cast<const uint2 *>(rd + 4);
+	h[0] = a.y; h[1] = a.z; h[2] = a.w; h[3] = b.x; h[4] = b.y;
+	if (cs0) { h[4] = b.x; h[3] = a.w; h[2] = a.z; h[1] = a.y; h[0] = a.x; }
+}
+
+// one fifth_order pass over the lane's M inputs -> M/2 outputs (src/rtl_fm.c:411-440); output j is the tap set over
+// inputs 2j-5 .. 2j of the level's sequence
+template <int M>
+__device__ __forceinline__ void row_level(uint32_t *xs, int carry_w, int carry_r, int lane, bool cs0,
+                                          const uint32_t (&in)[M], uint32_t (&out)[M / 2])
+{
+	uint32_t h[5];
+	row_exchange(xs, carry_w, carry_r, lane, cs0, in[M - 6], in[M - 5], in[M - 4], in[M - 3], in[M - 2], in[M - 1], h);
+	out[0] = hb_tap(h[0], h[1], h[2], h[3], h[4], in[0]);
+	out[1] = hb_tap(h[2], h[3], h[4], in[0], in[1], in[2]);
+	out[2] = hb_tap(h[4], in[0], in[1], in[2], in[3], in[4]);
+#pragma unroll
+	for (int j = 3; j < M / 2; j++) { out[j] = hb_tap(in[2 * j - 5], in[2 * j - 4], in[2 * j - 3], in[2 * j - 2], in[2 * j - 1], in[2 * j]); }
+}
+
+// generic_fir (src/rtl_fm.c:442-465) on nine explicit history words whose lanes are biased by FIR_B (see droop9_packed)
+__device__ __forceinline__ void droop9_words(const int (&c)[6], int fir_bias, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3,
+                                             uint32_t h4, uint32_t h5, uint32_t h6, uint32_t h7, uint32_t h8, int &di, int &dq)
+{
+	const uint32_t s0 = h0 + h8, s1 = h1 + h7, s2 = h2 + h6, s3 = h3 + h5, s4 = h4;
+	int ai = sub_w(mul_w((int)(s0 & 0xffffu), c[1]), fir_bias);
+	int aq = sub_w(mul_w((int)(s0 >> 16), c[1]), fir_bias);
+	ai = add_w(ai, mul_w((int)(s1 & 0xffffu), c[2])); aq = add_w(aq, mul_w((int)(s1 >> 16), c[2]));
+	ai = add_w(ai, mul_w((int)(s2 & 0xffffu), c[3])); aq = add_w(aq, mul_w((int)(s2 >> 16), c[3]));
+	ai = add_w(ai, mul_w((int)(s3 & 0xffffu), c[4])); aq = add_w(aq, mul_w((int)(s3 >> 16), c[4]));
+	ai = add_w(ai, mul_w((int)(s4 & 0xffffu), c[5])); aq = add_w(aq, mul_w((int)(s4 >> 16), c[5]));
+	di = wrap16(ai >> 15);
+	dq = wrap16(aq >> 15);
+}
+
+// Everything of one row after the scale: x = the lane's 32 samples scaled, rotated and packed (lanes biased by 128).
+// par = parity of the row (which carry slot lane 31 writes); cs = the row starts a chunk; rel = index of the lane's
+// first PCM sample in the item's shared PCM buffer.
+template <int P, bool FIR>
+__device__ __forceinline__ void row_body(const FmDev &c, uint32_t *xs, int par, int lane, bool cs, bool store,
+                                         const uint32_t (&x)[ROW_LANE], int16_t *pcm_s, int rel)
+{
+	typedef RowSmem<P> RS;
+	constexpr int NV = RS::NV;
+	const bool cs0 = cs && lane == 0;
+	uint32_t o[NV];                        // the lane's decimated samples, lanes biased by 128 << P
+	{
+		uint32_t y[ROW_LANE / 2];
+		row_level<ROW_LANE>(xs, RS::CARRY + (0 * 2 + par) * 8, RS::CARRY + (0 * 2 + (par ^ 1)) * 8, lane, cs0, x, y);
+		if constexpr (P == 1) {
+#pragma unroll
+			for (int j = 0; j < NV; j++) { o[j] = y[j]; }
+		} else {
+			uint32_t z[ROW_LANE / 4];
+			row_level<ROW_LANE / 2>(xs, RS::CARRY + (1 * 2 + par) * 8, RS::CARRY + (1 * 2 + (par ^ 1)) * 8, lane, cs0, y, z);
+			if constexpr (P == 2) {
+#pragma unroll
+				for (int j = 0; j < NV; j++) { o[j] = z[j]; }
+			} else {
+				row_level<ROW_LANE / 4>(xs, RS::CARRY + (2 * 2 + par) * 8, RS::CARRY + (2 * 2 + (par ^ 1)) * 8, lane, cs0, z, o);
+			}
+		}
+	}
+	constexpr int BO = 128 << P;
+	int di[NV], dq[NV];
+	if constexpr (FIR) {
+		// droop FIR over the previous nine decimated samples: the row's samples sit in a linear ring, twelve of the
+		// previous row in front, so lane l's history is simply the nine words before its own
+		uint32_t ob[NV];
+#pragma unroll
+		for (int j = 0; j < NV; j++) { ob[j] = o[j] + (FIR_B - (unsigned)BO) * 0x10001u; }
+		uint32_t *vr = xs + RS::VRING;
+		__syncwarp();
+#pragma unroll
+		for (int j = 0; j < NV; j += 4) { *reinterpret_cast<uint4 *>(vr + 12 + NV * lane + j) = make_uint4(ob[j], ob[j + 1], ob[j + 2], ob[j + 3]); }
+		__syncwarp();
+		uint32_t s[9 + NV];
+		{
+			const uint4 a = *reinterpret_cast<const uint4 *>(vr + NV * lane);
+			const uint4 b = *reinterpret_cast<const uint4 *>(vr + NV * lane + 4);
+			const uint4 d = *reinterpret_cast<const uint4 *>(vr + NV * lane + 8);
+			s[0] = a.w; s[1] = b.x; s[2] = b.y; s[3] = b.z; s[4] = b.w; s[5] = d.x; s[6] = d.y; s[7] = d.z; s[8] = d.w;
+		}
+#pragma unroll
+		for (int j = 0; j < NV; j++) { s[9 + j] = ob[j]; }
+#pragma unroll
+		for (int j = 0; j < NV; j++) {
+			droop9_words(c.fir, c.fir_bias, s[j], s[j + 1], s[j + 2], s[j + 3], s[j + 4], s[j + 5], s[j + 6], s[j + 7], s[j + 8], di[j], dq[j]);
+		}
+		__syncwarp();                      // every lane has its history: the ring's tail moves to the front for the next row
+		if (lane < 12) { vr[lane] = vr[32 * NV + lane]; }
+	} else {
+#pragma unroll
+		for (int j = 0; j < NV; j++) { di[j] = (int)(o[j] & 0xffffu) - BO; dq[j] = (int)(o[j] >> 16) - BO; }
+	}
+	// fm_demod (src/rtl_fm.c:584-615): x[n] * conj(x[n-1]) -> fast_atan2; the sample before the block is the neighbour's last
+	const uint32_t last = pack2(di[NV - 1], dq[NV - 1]);
+	uint32_t prev = __shfl_up_sync(0xffffffffu, last, 1);
+	if (lane == 31) { xs[RS::FPRE + par] = last; }
+	if (lane == 0) { prev = xs[RS::FPRE + (par ^ 1)]; }
+	int br = lo16(prev), bj = hi16(prev);
+	int pcm[NV];
+#pragma unroll
+	for (int j = 0; j < NV; j++) {
+		const int cr = add_w(mul_w(di[j], br), mul_w(dq[j], bj));
+		const int cj = sub_w(mul_w(dq[j], br), mul_w(di[j], bj));
+		pcm[j] = fast_atan2_i(cj, cr);
+		if (j == 0 && cs0) { pcm[0] = disc_std(cr, cj); }      // F8: the first sample of a chunk goes through atan2
+		br = di[j]; bj = dq[j];
+	}
+	if (store) {
+		int16_t *dst = pcm_s + pcm_phys(rel);
+#pragma unroll
+		for (int j = 0; j < NV; j += 4) {
+			uint2 w;
+			w.x = ((uint32_t)pcm[j] & 0xffffu) | ((uint32_t)pcm[j + 1] << 16);
+			w.y = ((uint32_t)pcm[j + 2] & 0xffffu) | ((uint32_t)pcm[j + 3] << 16);
+			*reinterpret_cast<uint2 *>(dst + j) = w;
+		}
+	}
+}
+
+// The rows [r0, r1) of one work item that this warp owns (rows are counted from the start of the channel's call).
+template <int P, bool FIR>
+__device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, const Item &it, int warp, int lane,
+                                           int16_t *pcm_s, uint32_t *xs)
+{
+	typedef RowSmem<P> RS;
+	constexpr int NV = RS::NV;
+	const long long rows_total = k.n / ROW_LEN;
+	const long long own_lo = (long long)it.b * k.n_own;
+	const long long own_hi = own_lo + k.n_own < rows_total ? own_lo + k.n_own : rows_total;
+	const long long buf_lo = own_lo - k.n_extra > 0 ? own_lo - k.n_extra : 0;
+	const int n_rows = (int)(own_hi - buf_lo);
+	const int per = (n_rows + k.fe_warps - 1) / k.fe_warps;
+	const long long r0 = buf_lo + (long long)warp * per;
+	const long long r1 = r0 + per < own_hi ? r0 + per : own_hi;
+	if (r0 >= r1) { return; }
+	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
+	const int16_t *in = k.in + 2 * (size_t)it.ch * (size_t)k.n;
+	const int rpc = k.chunk / ROW_LEN;              // rows per chunk
+	int par = 0;
+	// what the (non-existent) row before the first one left behind: the call's carry at the start of the stream,
+	// silence in front of a replayed row
+	__syncwarp();
+	if (r0 == 0) {
+		if (lane < 6) {
+#pragma unroll
+			for (int l = 0; l < P; l++) { xs[RS::CARRY + (l * 2 + 1) * 8 + lane] = carry[ST_HDR + 6 * l + lane]; }
+		}
+		if (FIR && lane < 9) { xs[RS::VRING + 3 + lane] = fir_bias_lanes(carry[ST_HDR + 6 * P + lane]); }
+		if (lane == 0) { xs[RS::FPRE + 1] = pack2((int)carry[ST_PRE_I], (int)carry[ST_PRE_Q]); }
+	} else {
+		if (lane < 6) {
+#pragma unroll
+			for (int l = 0; l < P; l++) { xs[RS::CARRY + (l * 2 + 1) * 8 + lane] = 0x00010001u * (128u << l); }
+		}
+		if (FIR && lane < 12) { xs[RS::VRING + lane] = fir_bias_lanes(0u); }
+		if (lane == 0) { xs[RS::FPRE + 1] = 0u; }
+	}
+	__syncwarp();
+	long long r = r0 == 0 ? 0 : r0 - 1;             // one replayed row makes every filter exact (the chain remembers 16 << P samples)
+	uint32_t v[ROW_LANE];
+	row_load(in + 2 * (size_t)r * ROW_LEN, lane, v, 0u);
+	for (; r < r1; r++) {
+		uint32_t x[ROW_LANE];
+#pragma unroll
+		for (int j = 0; j < ROW_LANE; j++) { x[j] = scale_rot_pack(v[j], j, true); }
+		// the raw block's registers are free from here on: the next row is loaded straight into them and has the
+		// rest of this row's work to arrive; the rows after it are pulled into L2 one line per lane
+		const long long rn = r + 1 < r1 ? r + 1 : r;
+		row_load(in + 2 * (size_t)rn * ROW_LEN, lane, v, x[ROW_LANE - 1]);
+		{
+			const long long rp = r + ROW_PF < rows_total ? r + ROW_PF : rows_total - 1;
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2 * (size_t)rp * ROW_LEN + 2 * ROW_LANE * lane));
+		}
+		const bool cs = (r % rpc) == 0;
+		const int rel = (int)(((r * ROW_LEN) >> P) - it.m_lo) + NV * lane;
+		row_body<P, FIR>(c, xs, par, lane, cs, r >= r0, x, pcm_s, rel);
+		par ^= 1;
+	}
+	if (r1 == rows_total) {
+		// this warp saw the end of the stream: lane 31's tails are the next call's carry (same layout as front_store)
+		__syncwarp();
+		uint32_t *co = k.carry_out + (size_t)it.ch * k.state_words;
+		const int pl = par ^ 1;                     // parity of the last row
+		if (lane < 6) {
+#pragma unroll
+			for (int l = 0; l < P; l++) { co[ST_HDR + 6 * l + lane] = xs[RS::CARRY + (l * 2 + pl) * 8 + lane]; }
+		}
+		if (FIR && lane < 9) { co[ST_HDR + 6 * P + lane] = fir_unbias_lanes(xs[RS::VRING + 3 + lane]); }
+		if (lane == 0) {
+			const uint32_t f = xs[RS::FPRE + pl];
+			co[ST_PRE_I] = (uint32_t)lo16(f); co[ST_PRE_Q] = (uint32_t)hi16(f);
+			co[ST_BOX_I] = 0u; co[ST_BOX_Q] = 0u; co[ST_BOX_N] = 0u;
+		}
+	}
+}

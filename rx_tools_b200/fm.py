@@ -152,7 +152,9 @@ class FmDemod:
     def stats(self) -> dict:
         s = _lib.FmStatsC()
         _lib.check(_lib.lib().rxb200_fm_last_stats(self._h, C.byref(s)))
-        return {f[0]: int(getattr(s, f[0])) for f in s._fields_}
+        d = {f[0]: int(getattr(s, f[0])) for f in s._fields_}
+        d["kernel"] = "fm_split_kernel" if d["kernel_kind"] == 1 else "fm_fused_kernel"
+        return d
 
 
 # ---- rx_sdr sample-format conversions (src/rtl_sdr.c:348-391) -------------------------------------------

@@ -51,6 +51,13 @@ def fm_cases(scale: int = 1) -> list[FmCase]:
     cs.append(FmCase("cfg2B_chunk65536", FmParams(downsample=8, downsample_passes=3, comp_fir_size=9,
                                                   custom_atan=ATAN_FAST, deemph=1, deemph_a=23, rate_out=300_000,
                                                   rate_out2=48_000), _wb(n), 65536))
+    # wbfm with one and two passes + droop FIR (-s 1200k / -s 600k -F 9): the row front end's P = 1, 2 instantiations
+    cs.append(FmCase("wbfm_P1_fir", FmParams(downsample=2, downsample_passes=1, comp_fir_size=9, custom_atan=ATAN_FAST,
+                                             deemph=1, deemph_a=91, rate_out=1_200_000, rate_out2=48_000), _wb(n, seed=41), C))
+    cs.append(FmCase("wbfm_P2_fir", FmParams(downsample=4, downsample_passes=2, comp_fir_size=9, custom_atan=ATAN_FAST,
+                                             deemph=1, deemph_a=46, rate_out=600_000, rate_out2=48_000), _wb(n, seed=42), C))
+    cs.append(FmCase("wbfm_P2_nofir", FmParams(downsample=4, downsample_passes=2, comp_fir_size=0, custom_atan=ATAN_FAST,
+                                               deemph=1, deemph_a=46, rate_out=600_000, rate_out2=48_000), _wb(n, seed=43), 65536))
     # -F 0: half-band passes without droop FIR, P=1 and P=5
     cs.append(FmCase("F0_P1", FmParams(downsample=2, downsample_passes=1, comp_fir_size=0, custom_atan=ATAN_FAST,
                                        rate_out=1_200_000, rate_out2=48_000), _wb(n, seed=3), C))

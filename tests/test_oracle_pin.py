@@ -48,7 +48,7 @@ def test_fm_levels_port_equals_reference(case, port, ref_fm):
     b = ref_fm.levels(case.params, x, case.chunk_int16)
     assert a.size == b.size and a.size >= 1
     assert np.array_equal(a, b)
-    assert b.max() > 0
+    assert b.max() > 0 or case.name.startswith("zeros")      # an all-zero capture has level 0
 
 
 def test_derivation_matches_optimal_settings(ref_fm):
