@@ -23,8 +23,10 @@
 #include <SoapySDR/Formats.h>
 
 struct SoapySDRDevice {
-	const int16_t *mem;     /* interleaved CS16 */
+	const int16_t *mem;     /* the capture: interleaved CS16 (or raw bytes of another element format, see elem_size) */
 	size_t n_complex;       /* total complex elements available */
+	size_t n_bytes;         /* the same capture in bytes (file replay) */
+	size_t elem_size;       /* bytes per complex element of the stream format: 4 (CS16) unless setupStream said CS12 (3) */
 	size_t pos;             /* next complex element */
 	int loop;
 	int owns_mem;
@@ -44,7 +46,7 @@ static int (*g_read_hook)(void * const *buffs, size_t numElems) = NULL;
 void soapy_fake_set_memory(const int16_t *cs16, size_t n_complex, int loop)
 {
 	if (g_dev.owns_mem) { free((void *)g_dev.mem); }
-	g_dev.mem = cs16; g_dev.n_complex = n_complex; g_dev.pos = 0;
+	g_dev.mem = cs16; g_dev.n_complex = n_complex; g_dev.n_bytes = n_complex * 4; g_dev.elem_size = 4; g_dev.pos = 0;
 	g_dev.loop = loop; g_dev.owns_mem = 0; g_dev.reads = 0;
 }
 void soapy_fake_set_read_hook(int (*hook)(void * const *buffs, size_t numElems)) { g_read_hook = hook; }
@@ -83,7 +85,7 @@ static int load_file(const char *path)
 	if (sz > 0 && fread(buf, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(buf); g_err = "fake: short read"; return -1; }
 	fclose(f);
 	if (g_dev.owns_mem) { free((void *)g_dev.mem); }
-	g_dev.mem = buf; g_dev.n_complex = (size_t)sz / 4; g_dev.pos = 0; g_dev.owns_mem = 1; g_dev.reads = 0;
+	g_dev.mem = buf; g_dev.n_bytes = (size_t)sz; g_dev.elem_size = 4; g_dev.n_complex = (size_t)sz / 4; g_dev.pos = 0; g_dev.owns_mem = 1; g_dev.reads = 0;
 	return 0;
 }
 
@@ -153,7 +155,12 @@ SoapySDRStream *SoapySDRDevice_setupStream(SoapySDRDevice *d, const int dir, con
 	const size_t *channels, const size_t numChans, const SoapySDRKwargs *args)
 {
 	(void)d; (void)dir; (void)channels; (void)numChans; (void)args;
-	if (!format || strcmp(format, SOAPY_SDR_CS16) != 0) { g_err = "fake: only CS16"; return NULL; }
+	/* CS16 is what rx_fm / rx_power ask for; rx_sdr may also ask for the packed 12-bit format (-I CS12,
+	 * src/rtl_sdr.c:352-362): the capture file is then taken as 3-byte elements */
+	if (format && strcmp(format, SOAPY_SDR_CS12) == 0) { g_dev.elem_size = 3; }
+	else if (format && strcmp(format, SOAPY_SDR_CS16) == 0) { g_dev.elem_size = 4; }
+	else { g_err = "fake: only CS16 and CS12"; return NULL; }
+	if (g_dev.n_bytes) { g_dev.n_complex = g_dev.n_bytes / g_dev.elem_size; }
 	return &g_stream;
 }
 int SoapySDRDevice_closeStream(SoapySDRDevice *d, SoapySDRStream *s) { (void)d; (void)s; return 0; }
@@ -177,7 +184,7 @@ int SoapySDRDevice_readStream(SoapySDRDevice *d, SoapySDRStream *s, void * const
 	}
 	avail = d->n_complex - d->pos;
 	n = numElems < avail ? numElems : avail;
-	memcpy(buffs[0], d->mem + 2 * d->pos, n * 4);
+	memcpy(buffs[0], (const unsigned char *)d->mem + d->elem_size * d->pos, n * d->elem_size);
 	d->pos += n;
 	return (int)n;
 }

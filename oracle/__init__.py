@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "librx_oracle.so")
 REF_FM_SO = os.path.join(HERE, "_ref", "libref_fm.so")
 REF_POWER_SO = os.path.join(HERE, "_ref", "libref_power.so")
+REF_SDR_BIN = os.path.join(HERE, "_ref", "rx_sdr_ref")
 REFERENCE_ROOT = "/root/reference"
 
 MODE_FM, MODE_AM, MODE_USB, MODE_LSB, MODE_RAW = range(5)
@@ -428,6 +429,22 @@ class RefPower:
         buf = _i16(iq).copy()
         self.L.ref_fix_fft(_p16(buf), m, m if log2_wave is None else log2_wave)
         return buf
+
+
+def ref_rx_sdr(src: np.ndarray, in_fmt: str, out_fmt: str, n_elems: int, block: int = 16384, workdir: str = "/tmp") -> bytes:
+    """Run the reference's own rx_sdr executable (_ref/rx_sdr_ref = src/rtl_sdr.c's main() linked against the replay
+    fake) over a capture and return the bytes it wrote: `rx_sdr -d driver=file,path=.. -I in_fmt -F out_fmt -n N -b B out`.
+    The capture must hold MORE than n_elems elements (the recorder only stops on a read that over-delivers, :341-346)."""
+    import tempfile
+    with tempfile.TemporaryDirectory(dir=workdir) as td:
+        cap, out = os.path.join(td, "cap.bin"), os.path.join(td, "out.bin")
+        np.ascontiguousarray(src).tofile(cap)
+        r = subprocess.run([REF_SDR_BIN, "-d", f"driver=file,path={cap}", "-I", in_fmt, "-F", out_fmt, "-n", str(n_elems),
+                            "-b", str(block), out], capture_output=True, timeout=120)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr.decode()[-500:])
+        with open(out, "rb") as f:
+            return f.read()
 
 
 _port: Optional[Port] = None

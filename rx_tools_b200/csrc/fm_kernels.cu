@@ -408,11 +408,13 @@ __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int
 	if (!c.resample) { return m; }
 	return ((long long)phase0 + m * (long long)c.slow) / (long long)c.fast;
 }
-// shared PCM buffer: 16 bytes of padding per 128 entries so that neither the front-end stores
-// (thread stride ~ Sf/D entries) nor the back-end loads (lane stride = piece) pile on one bank; 16 keeps
-// the row front end's 8/16-byte vector stores aligned (fm_rows.cuh)
-#define PCM_PAD 8
-__device__ __forceinline__ int pcm_phys(int rel) { return rel + PCM_PAD * (rel >> 7); }
+// shared PCM buffer: PAD entries of padding per 128 so that neither the front-end stores (thread stride ~ Sf/D
+// entries) nor the back-end loads (lane stride = piece) pile on one bank.  The segment front end uses 2 (4 bytes);
+// the row front end 8, which keeps its 8/16-byte vector stores aligned (fm_rows.cuh)
+#define PCM_PAD_SEG 2
+#define PCM_PAD_ROWS 8
+template <int PAD>
+__device__ __forceinline__ int pcm_phys(int rel) { return rel + PAD * (rel >> 7); }
 
 // Compile-time specialisation of the flags that sit in the per-sample path.  SPEC 0: everything is a
 // (warp-uniform) run-time branch.  SPEC 1: the wbfm shape — FM discriminator with fast_atan2, fs/4
@@ -488,7 +490,7 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 	}
 	if (STORE) {      // the int16 store is the reference's (int16_t) cast
 		if (Spec<SPEC>::direct(k)) { if (SPEC != 2 || k.reduce_mode == 0) { e.out[e.m_lo + e.rel] = (int16_t)pcm; } }
-		else { e.pcm[pcm_phys(e.rel)] = (int16_t)pcm; }
+		else { e.pcm[pcm_phys<PCM_PAD_SEG>(e.rel)] = (int16_t)pcm; }
 	}
 	e.rel++;
 }
@@ -631,11 +633,12 @@ __device__ __forceinline__ int deemph_fast(int avg, int x, int xb, unsigned magi
 	return avg + (int)__umulhi((unsigned)n, magic) - K;
 }
 
-__device__ __forceinline__ int pcm_load(const int16_t *pcm_s, int m) { return (int)pcm_s[pcm_phys(m)]; }
+template <int PAD>
+__device__ __forceinline__ int pcm_load(const int16_t *pcm_s, int m) { return (int)pcm_s[pcm_phys<PAD>(m)]; }
 
 // deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a
 // piece).  The two trajectories are independent, the next sample is fetched one step ahead.
-template <bool EVEN>
+template <bool EVEN, int PAD>
 __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
 {
 	if (m >= m_end) { return; }
@@ -644,13 +647,13 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 	if (c.a_use_magic) {
 		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
 		for (; (m & 3) != 0 && m < m_end; m++) {
-			const int x = pcm_load(pcm_s, m);
+			const int x = pcm_load<PAD>(pcm_s, m);
 			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
 			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
 		}
 #pragma unroll 2
 		for (; m + 4 <= m_end; m += 4) {
-			const int16_t *q = pcm_s + pcm_phys(m);
+			const int16_t *q = pcm_s + pcm_phys<PAD>(m);
 			const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
 			lo = deemph_fast<EVEN>(lo, x0, x0 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x0, x0 + bias, magic, K);
 			lo = deemph_fast<EVEN>(lo, x1, x1 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x1, x1 + bias, magic, K);
@@ -658,13 +661,13 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 			lo = deemph_fast<EVEN>(lo, x3, x3 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x3, x3 + bias, magic, K);
 		}
 		for (; m < m_end; m++) {
-			const int x = pcm_load(pcm_s, m);
+			const int x = pcm_load<PAD>(pcm_s, m);
 			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
 			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
 		}
 	} else {
 		for (; m < m_end; m++) {
-			const int x = pcm_load(pcm_s, m);
+			const int x = pcm_load<PAD>(pcm_s, m);
 			lo = deemph_step(c, lo, x);
 			hi = deemph_step(c, hi, x);
 		}
@@ -674,14 +677,14 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 // What a piece does to the states of an open bracket [lo, hi]: both ends are run through PCM [m, m_end);
 // returns non-zero when either end moved at any step.
 enum { PK_OPEN = 0, PK_EXACT = 1, PK_MERGED = 2, PK_IDENT = 3 };
-template <bool EVEN>
+template <bool EVEN, int PAD>
 __device__ __forceinline__ int back_probe(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
 {
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
 	int moved = 0;
 	for (; m < m_end; m++) {
-		const int x = pcm_load(pcm_s, m);
+		const int x = pcm_load<PAD>(pcm_s, m);
 		int nl, nh;
 		if (c.a_use_magic) { nl = deemph_fast<EVEN>(lo, x, x + bias, magic, K); nh = deemph_fast<EVEN>(hi, x, x + bias, magic, K); }
 		else { nl = deemph_step(c, lo, x); nh = deemph_step(c, hi, x); }
@@ -723,7 +726,7 @@ __device__ __forceinline__ int adc_apply(const FmDev &c, AdcCtx &a, int m_rel, i
 // group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
 // group a call inherits from the previous call can start with a larger phase).
 // m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
-template <bool EVEN>
+template <bool EVEN, int PAD>
 __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out,
                                              long long oa, long long ob, int &m, int &avg, int acc, int phase,
                                              AdcCtx *ax, bool store)
@@ -732,7 +735,7 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 	const unsigned magic = c.a_magic;
 	const int lf = c.resample ? c.fast / c.slow : 1;
 	const bool fast_path = c.deemph && c.a_use_magic;
-	int x = (oa < ob) ? pcm_load(pcm_s, m) : 0;
+	int x = (oa < ob) ? pcm_load<PAD>(pcm_s, m) : 0;
 	for (long long o = oa; o < ob; o++) {
 		int len = 1;
 		if (c.resample) {
@@ -741,7 +744,7 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 			phase += len * c.slow - c.fast;
 		}
 		for (int j = 0; j < len; j++) {
-			int xn = pcm_load(pcm_s, m + 1);      // one entry of slack exists past the last sample
+			int xn = pcm_load<PAD>(pcm_s, m + 1);      // one entry of slack exists past the last sample
 			if (fast_path) { avg = deemph_fast<EVEN>(avg, x, x + bias, magic, K); x = wrap16(avg); }
 			else if (c.deemph) { avg = deemph_step(c, avg, x); x = wrap16(avg); }
 			if (ax) { x = adc_apply(c, *ax, m, x); }
@@ -930,12 +933,13 @@ __device__ __forceinline__ Piece make_piece(const FmDev &c, const Item &it, cons
 	return p;
 }
 
+template <int PAD>
 __device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, const Piece &p,
                                           int &m_run, int &avg, AdcCtx *ax, bool store)
 {
 	m_run = p.ga;
-	if (c.a_even) { back_outputs<true>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
-	else { back_outputs<false>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
+	if (c.a_even) { back_outputs<true, PAD>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
+	else { back_outputs<false, PAD>(c, pcm_s, out, p.oa, p.ob, m_run, avg, p.acc0, p.ph0, ax, store); }
 	if (ax) { adc_flush(*ax); }
 }
 
@@ -943,7 +947,7 @@ __device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, 
 #define BAR_BE 1                 // named barrier of the back-end warps (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int SPEC>
+template <int SPEC, int PAD>
 __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
                                           const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok, int *s_start)
 {
@@ -975,7 +979,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 			ws &= ~3;           // quad-aligned start: a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
 			if (it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
 			if (c.deemph) {
-				if (c.a_even) { back_replay<true>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false>(c, pcm_s, ws, p.ga, lo, hi); }
+				if (c.a_even) { back_replay<true, PAD>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false, PAD>(c, pcm_s, ws, p.ga, lo, hi); }
 			}
 			avg = lo;
 			if (c.deemph && lo != hi) {
@@ -984,12 +988,12 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 				// whatever the start was; if neither ever moves, no state in between moves either (the fixed
 				// points of one step form an interval), so the piece passes its start state through.
 				const int ge = active ? (int)(group_start(c, p.ob, it.phase0) - it.m_lo) : p.ga;
-				const int moved = c.a_even ? back_probe<true>(c, pcm_s, p.ga, ge, lo, hi) : back_probe<false>(c, pcm_s, p.ga, ge, lo, hi);
+				const int moved = c.a_even ? back_probe<true, PAD>(c, pcm_s, p.ga, ge, lo, hi) : back_probe<false, PAD>(c, pcm_s, p.ga, ge, lo, hi);
 				kind = (lo == hi) ? PK_MERGED : (moved == 0 ? PK_IDENT : PK_OPEN);
 				avg = lo; m_run = ge;
 			}
 		}
-		if (active && kind == PK_EXACT) { run_piece(c, pcm_s, out, p, m_run, avg, ax, store); }
+		if (active && kind == PK_EXACT) { run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store); }
 		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = (unsigned char)kind;
 	}
 	bar_sync(BAR_BE, lanes);
@@ -1003,7 +1007,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 			int l2 = start, h2 = start;
 			if (pj.oa < pj.ob) {
 				const int ge = (int)(group_start(c, pj.ob, it.phase0) - it.m_lo);
-				if (c.a_even) { back_probe<true>(c, pcm_s, pj.ga, ge, l2, h2); } else { back_probe<false>(c, pcm_s, pj.ga, ge, l2, h2); }
+				if (c.a_even) { back_probe<true, PAD>(c, pcm_s, pj.ga, ge, l2, h2); } else { back_probe<false, PAD>(c, pcm_s, pj.ga, ge, l2, h2); }
 			}
 			return l2;
 		};
@@ -1054,7 +1058,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	// ---- pass 2: the pieces that had no exact start in pass 1 now run from the state the chain gave them
 	if (active && kind != PK_EXACT) {
 		int avg = s_start[q], m_run = p.ga;
-		run_piece(c, pcm_s, out, p, m_run, avg, ax, store);
+		run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store);
 	}
 	if (q != 0) { return; }
 	// end state of the item = state after its last piece
@@ -1064,7 +1068,7 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		// tail of the stream: samples after the last emitted output stay in the accumulator
 		int acc = (it.m_lo == 0 && fin_m == 0) ? (int)carry[ST_LPR_ACC] : 0;
 		for (int m = fin_m; m < it.m_hi; m++) {
-			int x = (int)pcm_s[pcm_phys(m)];
+			int x = (int)pcm_s[pcm_phys<PAD>(m)];
 			if (c.deemph) { fin_avg = deemph_step(c, fin_avg, x); x = wrap16(fin_avg); }
 			if (ax) { x = adc_apply(c, *ax, m, x); }
 			acc = add_w(acc, x);
@@ -1111,7 +1115,7 @@ __global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3
 			continue;
 		}
 		__syncthreads();
-		if (tid < k.be_lanes) { back_item<SPEC>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok, s_start); }
+		if (tid < k.be_lanes) { back_item<SPEC, PCM_PAD_SEG>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok, s_start); }
 	}
 }
 
@@ -1137,6 +1141,8 @@ __global__ void __launch_bounds__(TMAX, MINB) fm_split_kernel(const FmDev c, con
 	__shared__ unsigned char s_ok[SPLIT_BE_MAX];
 	const int tid = threadIdx.x;
 	const int n_fe = k.fe_threads;
+	int lane;
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));     // volatile: read once (the compiler would re-read the special register at every use)
 	if (tid == 0) {
 		mbar_init(&s_full[0], n_fe); mbar_init(&s_full[1], n_fe);
 		mbar_init(&s_empty[0], k.be_lanes); mbar_init(&s_empty[1], k.be_lanes);
@@ -1156,7 +1162,7 @@ __global__ void __launch_bounds__(TMAX, MINB) fm_split_kernel(const FmDev c, con
 			if constexpr (FE == 0) { front_item<P, SPEC>(c, k, it, tid, buf); }
 			else {
 				uint32_t *xs = reinterpret_cast<uint32_t *>(pcm_s + 2 * (size_t)k.pcm_cap) + (size_t)(tid >> 5) * k.xs_words;
-				front_rows<P, FE == 1>(c, k, it, tid >> 5, tid & 31, buf, xs);
+				front_rows<P, FE == 1>(c, k, it, tid >> 5, lane, buf, xs);
 			}
 			mbar_arrive(&s_full[b]);
 		}
@@ -1168,7 +1174,7 @@ __global__ void __launch_bounds__(TMAX, MINB) fm_split_kernel(const FmDev c, con
 			const int work = s_ticket[b];
 			if (work >= total_work) { break; }
 			const Item it = make_item(c, k, work);
-			back_item<SPEC>(c, k, it, work, q, k.be_lanes, pcm_s + (size_t)b * k.pcm_cap, s_avg, s_mrun, s_ok, s_start);
+			back_item<SPEC, FE == 0 ? PCM_PAD_SEG : PCM_PAD_ROWS>(c, k, it, work, q, k.be_lanes, pcm_s + (size_t)b * k.pcm_cap, s_avg, s_mrun, s_ok, s_start);
 			mbar_arrive(&s_empty[b]);
 		}
 	}
@@ -1297,9 +1303,18 @@ static fm_kernel_fn pick_kernel_p(int P, int threads)
 }
 
 // the split kernel with the row front end exists for the wbfm shape with 1..3 packed passes
+// CTA shape of the split kernel (overridable for A/B builds, tools/build_variants.sh): front-end warps, back-end lanes,
+// CTAs per SM the register budget is cut for
+#ifndef ROWS_FE_WARPS
 #define ROWS_FE_WARPS 8
-#define ROWS_TMAX (ROWS_FE_WARPS * 32 + 32)
+#endif
+#ifndef ROWS_BE_LANES
+#define ROWS_BE_LANES 64
+#endif
+#ifndef ROWS_MINB
 #define ROWS_MINB 2
+#endif
+#define ROWS_TMAX (ROWS_FE_WARPS * 32 + ROWS_BE_LANES)
 static fm_kernel_fn pick_rows_kernel(int P, int fir_on)
 {
 #ifdef RXB_QUICK
@@ -1455,7 +1470,7 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		h->spec = spec;
 		const int fir_on = (params->downsample_passes > 0 && params->comp_fir_size == 9) ? 1 : 0;
 		h->kern_rows = (spec == 1 && !getenv("RXB200_FM_NOROWS")) ? pick_rows_kernel(params->downsample_passes, fir_on) : nullptr;
-		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = 32;
+		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = ROWS_BE_LANES;
 		{
 			// A/B knobs, read once at create: back-end lanes (32 | 64 ...) of the split kernel
 			const char *e = getenv("RXB200_FM_ROWS_BE");
@@ -1625,10 +1640,10 @@ static int fm_launch_rows(rxb200_fm *h, const int16_t *d_in, size_t n_int16, siz
 	if (dyn_max > h->smem_optin - (long long)fa.sharedSizeBytes) { dyn_max = h->smem_optin - (long long)fa.sharedSizeBytes; }
 	auto cap_for = [&](long long rows_item) -> long long {
 		long long e = rows_item * row_pcm + 8;              // one entry of slack is read past the last sample (back_outputs)
-		e += PCM_PAD * (e >> 7) + 16;
+		e += PCM_PAD_ROWS * (e >> 7) + 16;
 		return (e + 7) & ~7LL;                               // the second buffer and the exchange areas stay 16-byte aligned
 	};
-	long long rows_item = ((dyn_max - (long long)xs_bytes) / 2 / (long long)sizeof(int16_t)) / (row_pcm + (row_pcm * PCM_PAD) / 128 + 1);
+	long long rows_item = ((dyn_max - (long long)xs_bytes) / 2 / (long long)sizeof(int16_t)) / (row_pcm + (row_pcm * PCM_PAD_ROWS) / 128 + 1);
 	while (rows_item > rows_margin + 1 && 2 * cap_for(rows_item) * (long long)sizeof(int16_t) + (long long)xs_bytes > dyn_max) { rows_item--; }
 	long long rows_own = rows_item - rows_margin;
 	if (rows_own < 1) { set_error("the back-end replay (%lld PCM samples) does not fit the split kernel's PCM buffers", margin_dec); return RXB200_EUNSUPPORTED; }
@@ -1725,7 +1740,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		n_extra = direct_out ? 0 : (margin_dec * Dpcm + halo + sf - 1) / sf;
 		ppt = sf / Dpcm + 2;
 		pcm_cap = direct_out ? 8 : (long long)T * ppt + 64;
-		pcm_cap += PCM_PAD * (pcm_cap >> 7) + 16;
+		pcm_cap += PCM_PAD_SEG * (pcm_cap >> 7) + 8;
 		smem = (size_t)pcm_cap * sizeof(int16_t);
 		if ((long long)smem > h->smem_optin || n_extra > T / 2) { return false; }
 		n_own = T - n_extra;

@@ -18,13 +18,16 @@
 
 #define ROW_LANE 32                    // input samples per lane per row
 #define ROW_LEN (32 * ROW_LANE)        // input samples per warp row
+#ifndef ROW_PF
 #define ROW_PF 3                       // L2 prefetch distance in rows
+#endif
 
 template <int P>
 struct RowSmem {                       // word offsets inside a warp's exchange area
 	static constexpr int NV = ROW_LANE >> P;                 // decimated samples per lane per row
-	static constexpr int SLOT = 0;                           // [32][8]: slot l+1 = tail of lane l (six words used)
-	static constexpr int CARRY = 256;                        // [3 levels][2 parities][8]: lane 31's tail of a row
+	static constexpr int SLOTQ = 0;                          // uint4[32]: words 0..3 of lane l's tail at index l + 1
+	static constexpr int SLOTD = 128;                        // uint2[32]: words 4..5 (two arrays: no bank conflicts at 16 / 8 byte strides)
+	static constexpr int CARRY = 192;                        // [3 levels][2 parities][8]: lane 31's tail of a row
 	static constexpr int VRING = CARRY + 48;                 // [12 + 32 NV]: droop FIR inputs, 12 of the previous row first
 	static constexpr int FPRE = VRING + 12 + 32 * NV;        // [2 parities]: last FIR output of a row (raw I/Q pair)
 	static constexpr int WORDS = FPRE + 4;
@@ -47,26 +50,31 @@ __device__ __forceinline__ void row_load(const int16_t *in_row, int lane, uint32
 
 // hand the level's tail (its last six inputs, oldest first) to the next lane and fetch the five inputs before this
 // lane's block.  cs0: lane 0 of a chunk's first row -- the pass forgot its pending odd sample, the history is one older.
-__device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carry_r, int lane, bool cs0,
+// cs_trip: 1 on lane 0 of a chunk's first row, else 0 -- the trip count of a loop, so that the rare case is a branch
+// and not five predicated moves in every row.
+__device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carry_r, int lane, int cs_trip,
                                              uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
                                              uint32_t (&h)[5])
 {
 	__syncwarp();                          // the slots' previous readers are done
-	uint32_t *wr = (lane == 31) ? xs + carry_w : xs + 8 * (lane + 1);
-	*reinterpret_cast<uint4 *>(wr) = make_uint4(t0, t1, t2, t3);
-	*reinterpret_cast<uint2 *>(wr + 4) = make_uint2(t4, t5);
+	uint32_t *wq = (lane == 31) ? xs + carry_w : xs + 4 * (lane + 1);
+	uint32_t *wd = (lane == 31) ? xs + carry_w + 4 : xs + 128 + 2 * (lane + 1);
+	*reinterpret_cast<uint4 *>(wq) = make_uint4(t0, t1, t2, t3);
+	*reinterpret_cast<uint2 *>(wd) = make_uint2(t4, t5);
 	__syncwarp();
-	const uint32_t *rd = (lane == 0) ? xs + carry_r : xs + 8 * lane;
-	const uint4 a = *reinterpret_cast<const uint4 *>(rd);
-	const uint2 b = *reinterpret_cast<const uint2 *>(rd + 4);
+	const uint32_t *rq = (lane == 0) ? xs + carry_r : xs + 4 * lane;
+	const uint32_t *rd = (lane == 0) ? xs + carry_r + 4 : xs + 128 + 2 * lane;
+	const uint4 a = *reinterpret_cast<const uint4 *>(rq);
+	const uint2 b = *reinterpret_cast<const uint2 *>(rd);
 	h[0] = a.y; h[1] = a.z; h[2] = a.w; h[3] = b.x; h[4] = b.y;
-	if (cs0) { h[4] = b.x; h[3] = a.w; h[2] = a.z; h[1] = a.y; h[0] = a.x; }
+#pragma unroll 1
+	for (int z = 0; z < cs_trip; z++) { h[4] = b.x; h[3] = a.w; h[2] = a.z; h[1] = a.y; h[0] = a.x; }
 }
 
 // one fifth_order pass over the lane's M inputs -> M/2 outputs (src/rtl_fm.c:411-440); output j is the tap set over
 // inputs 2j-5 .. 2j of the level's sequence
 template <int M>
-__device__ __forceinline__ void row_level(uint32_t *xs, int carry_w, int carry_r, int lane, bool cs0,
+__device__ __forceinline__ void row_level(uint32_t *xs, int carry_w, int carry_r, int lane, int cs0,
                                           const uint32_t (&in)[M], uint32_t (&out)[M / 2])
 {
 	uint32_t h[5];
@@ -96,13 +104,13 @@ __device__ __forceinline__ void droop9_words(const int (&c)[6], int fir_bias, ui
 // Everything of one row after the scale: x = the lane's 32 samples scaled, rotated and packed (lanes biased by 128).
 // par = parity of the row (which carry slot lane 31 writes); cs = the row starts a chunk; rel = index of the lane's
 // first PCM sample in the item's shared PCM buffer.
+// Returns a word that depends on the row's last results (the caller hangs the next row's prefetched registers on it).
 template <int P, bool FIR>
-__device__ __forceinline__ void row_body(const FmDev &c, uint32_t *xs, int par, int lane, bool cs, bool store,
-                                         const uint32_t (&x)[ROW_LANE], int16_t *pcm_s, int rel)
+__device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int par, int lane, int cs0, bool store,
+                                             const uint32_t (&x)[ROW_LANE], int16_t *pcm_s, int rel)
 {
 	typedef RowSmem<P> RS;
 	constexpr int NV = RS::NV;
-	const bool cs0 = cs && lane == 0;
 	uint32_t o[NV];                        // the lane's decimated samples, lanes biased by 128 << P
 	{
 		uint32_t y[ROW_LANE / 2];
@@ -165,11 +173,14 @@ __device__ __forceinline__ void row_body(const FmDev &c, uint32_t *xs, int par, 
 		const int cr = add_w(mul_w(di[j], br), mul_w(dq[j], bj));
 		const int cj = sub_w(mul_w(dq[j], br), mul_w(di[j], bj));
 		pcm[j] = fast_atan2_i(cj, cr);
-		if (j == 0 && cs0) { pcm[0] = disc_std(cr, cj); }      // F8: the first sample of a chunk goes through atan2
+		if (j == 0) {
+#pragma unroll 1
+			for (int z = 0; z < cs0; z++) { pcm[0] = disc_std(cr, cj); }      // F8: the first sample of a chunk goes through atan2
+		}
 		br = di[j]; bj = dq[j];
 	}
 	if (store) {
-		int16_t *dst = pcm_s + pcm_phys(rel);
+		int16_t *dst = pcm_s + pcm_phys<PCM_PAD_ROWS>(rel);
 #pragma unroll
 		for (int j = 0; j < NV; j += 4) {
 			uint2 w;
@@ -178,6 +189,7 @@ __device__ __forceinline__ void row_body(const FmDev &c, uint32_t *xs, int par, 
 			*reinterpret_cast<uint2 *>(dst + j) = w;
 		}
 	}
+	return (uint32_t)pcm[NV - 1];
 }
 
 // The rows [r0, r1) of one work item that this warp owns (rows are counted from the start of the channel's call).
@@ -234,10 +246,17 @@ __device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, cons
 			const long long rp = r + ROW_PF < rows_total ? r + ROW_PF : rows_total - 1;
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2 * (size_t)rp * ROW_LEN + 2 * ROW_LANE * lane));
 		}
-		const bool cs = (r % rpc) == 0;
+		const int cs0 = ((r % rpc) == 0 && lane == 0) ? k.one : 0;
 		const int rel = (int)(((r * ROW_LEN) >> P) - it.m_lo) + NV * lane;
-		row_body<P, FIR>(c, xs, par, lane, cs, r >= r0, x, pcm_s, rel);
+		const uint32_t token = row_body<P, FIR>(c, xs, par, lane, cs0, r >= r0, x, pcm_s, rel);
 		par ^= 1;
+		// keep the prefetched row in the registers it was loaded into until here: left alone, the compiler copies some
+		// of them right behind the loads and the warp then sits out the whole memory latency
+#pragma unroll
+		for (int q = 0; q < ROW_LANE; q += 8) {
+			asm volatile("" : "+r"(v[q]), "+r"(v[q + 1]), "+r"(v[q + 2]), "+r"(v[q + 3]), "+r"(v[q + 4]), "+r"(v[q + 5]), "+r"(v[q + 6]), "+r"(v[q + 7])
+			             : "r"(token));
+		}
 	}
 	if (r1 == rows_total) {
 		// this warp saw the end of the stream: lane 31's tails are the next call's carry (same layout as front_store)
