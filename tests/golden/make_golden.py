@@ -62,7 +62,19 @@ def main():
     avg, smp = rp.scan(hb, 2)
     np.savez_compressed(os.path.join(HERE, "literal_vectors.npz"), fm_in=x, fm_out=y, fm_chunk=np.int64(2048),
                         pw_in=hb, pw_avg=avg, pw_samples=smp)
-    print("wrote", len(fm), "fm and", len(pw), "power golden entries")
+    # rx_sdr (src/rtl_sdr.c:348-391): the reference's own executable over a capture that holds every int16 value
+    import sdr_inputs as SI
+    sd = {}
+    x = SI.cs16_capture()
+    for fmt in ("CS8", "CU8", "CF32"):
+        b = oracle.ref_rx_sdr(x, "CS16", fmt, SI.N_ELEMS)
+        sd["CS16_" + fmt] = dict(input_sha256=digest(x), n_elems=SI.N_ELEMS, output_sha256=digest(np.frombuffer(b, dtype=np.uint8)), n_bytes=len(b))
+    y = SI.cs12_capture()
+    b = oracle.ref_rx_sdr(y, "CS12", "CS16", SI.N_ELEMS_12)
+    sd["CS12_CS16"] = dict(input_sha256=digest(y), n_elems=SI.N_ELEMS_12, output_sha256=digest(np.frombuffer(b, dtype=np.uint8)), n_bytes=len(b))
+    with open(os.path.join(HERE, "sdr_golden.json"), "w") as f:
+        json.dump(sd, f, indent=1, sort_keys=True)
+    print("wrote", len(fm), "fm,", len(pw), "power and", len(sd), "sdr golden entries")
 
 
 if __name__ == "__main__":

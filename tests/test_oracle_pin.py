@@ -3,6 +3,7 @@
 The reference ships no tests or golden vectors, so the reference code itself,
 executed, is the pin.  These tests need oracle/_ref (built here from /root/reference)."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -111,3 +112,49 @@ def test_fix_fft_port_equals_reference(m, port, ref_power):
     if m > 2:
         iq2 = iq[: 2 << (m - 2)]
         assert np.array_equal(port.fix_fft(iq2, m - 2, m), ref_power.fix_fft(iq2, m - 2, m))
+
+
+# ---- rx_sdr conversions (src/rtl_sdr.c:348-391): they live inline in main(), so the pin is the reference's own
+# executable (oracle/_ref/rx_sdr_ref) recording from the replay device
+def _port_sdr(port, name, src, dst, count):
+    import ctypes as C
+    f = getattr(port.L, name)
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    f.restype = None
+    f(src.ctypes.data, count, dst.ctypes.data)
+    return dst
+
+
+@pytest.mark.ref
+def test_sdr_conversions_port_equals_reference_executable(port):
+    import oracle
+    import sdr_inputs as SI
+    if not os.path.exists(oracle.REF_SDR_BIN):
+        pytest.skip("oracle/_ref/rx_sdr_ref not built (no /root/reference here)")
+    x = SI.cs16_capture()
+    n = SI.N_ELEMS
+    for fmt, name, dt in (("CS8", "orx_sdr_cs16_to_cs8", np.uint8), ("CU8", "orx_sdr_cs16_to_cu8", np.uint8),
+                          ("CF32", "orx_sdr_cs16_to_cf32", np.float32)):
+        ref = np.frombuffer(oracle.ref_rx_sdr(x, "CS16", fmt, n), dtype=np.uint8)
+        mine = _port_sdr(port, name, np.ascontiguousarray(x[:2 * n]), np.empty(2 * n, dt), 2 * n)
+        assert np.array_equal(ref, mine.view(np.uint8)), fmt
+    y = SI.cs12_capture()
+    n12 = SI.N_ELEMS_12
+    ref = np.frombuffer(oracle.ref_rx_sdr(y, "CS12", "CS16", n12), dtype=np.int16)
+    assert np.array_equal(ref, _port_sdr(port, "orx_sdr_cs12_to_cs16", y, np.empty(2 * n12, np.int16), n12))
+
+
+def test_sdr_conversions_port_equals_golden(port):
+    import json
+    import sdr_inputs as SI
+    from rx_tools_b200.synth import digest
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdr_golden.json")))
+    x, n = SI.cs16_capture(), SI.N_ELEMS
+    assert digest(x) == g["CS16_CS8"]["input_sha256"]
+    for fmt, name, dt in (("CS8", "orx_sdr_cs16_to_cs8", np.uint8), ("CU8", "orx_sdr_cs16_to_cu8", np.uint8),
+                          ("CF32", "orx_sdr_cs16_to_cf32", np.float32)):
+        mine = _port_sdr(port, name, np.ascontiguousarray(x[:2 * n]), np.empty(2 * n, dt), 2 * n)
+        assert digest(mine.view(np.uint8)) == g["CS16_" + fmt]["output_sha256"], fmt
+    y, n12 = SI.cs12_capture(), SI.N_ELEMS_12
+    mine = _port_sdr(port, "orx_sdr_cs12_to_cs16", y, np.empty(2 * n12, np.int16), n12)
+    assert digest(mine.view(np.uint8)) == g["CS12_CS16"]["output_sha256"]

@@ -37,3 +37,21 @@ def test_cs12_unpack():
     rng = np.random.default_rng(12)
     b = rng.integers(0, 256, size=3 * 10007, dtype=np.int32).astype(np.uint8)
     assert np.array_equal(fm.sdr_convert(fm.CVT_CS12_CS16, b), _port("orx_sdr_cs12_to_cs16", b, np.empty(2 * 10007, np.int16)))
+
+
+def test_against_the_reference_executable_golden():
+    """tests/golden/sdr_golden.json: what the reference's own rx_sdr (oracle/_ref/rx_sdr_ref, src/rtl_sdr.c's main()
+    recording from the replay device) wrote for these captures -- every int16 value, and random packed CS12."""
+    import json
+    import os
+    import sdr_inputs as SI
+    from rx_tools_b200.synth import digest
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdr_golden.json")))
+    x = np.ascontiguousarray(SI.cs16_capture()[: 2 * SI.N_ELEMS])
+    for kind, key in ((fm.CVT_CS16_CS8, "CS16_CS8"), (fm.CVT_CS16_CU8, "CS16_CU8"), (fm.CVT_CS16_CF32, "CS16_CF32")):
+        got = fm.sdr_convert(kind, x)
+        assert got.nbytes == g[key]["n_bytes"]
+        assert digest(got.view(np.uint8)) == g[key]["output_sha256"], key
+    y = np.ascontiguousarray(SI.cs12_capture()[: 3 * SI.N_ELEMS_12])
+    got = fm.sdr_convert(fm.CVT_CS12_CS16, y)
+    assert digest(got.view(np.uint8)) == g["CS12_CS16"]["output_sha256"]
