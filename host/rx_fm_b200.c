@@ -81,6 +81,7 @@ static struct {
 	int print_levels, level_no, level_max, level_max_max; double level_sum;   /* -L (src/rtl_fm.c:96-100) */
 	volatile int mute;                 /* int16 to zero at the start of the next read */
 	size_t multiple;                   /* chunk granularity librxb200 accepts */
+	int failed;                        /* a library call failed: exit status 1 */
 	rxb200_fm *fm;
 	FILE *out;
 	Queue q_raw, q_pcm;
@@ -138,21 +139,29 @@ static void write_wav_header(void)
 static void *reader_thread(void *arg)
 {
 	(void)arg;
+	/* what a read left over past the library's chunk granularity is carried into the next slot, never dropped: the
+	 * stream stays continuous whatever lengths the device returns (the reference hands any length on, :894-899) */
+	static int16_t rem[4096];
+	size_t rem_n = 0;
 	SoapySDRDevice_activateStream(G.dev, G.stream, 0, 0, 0);
 	for (;;) {
 		Slot *s = q_begin_put(&G.q_raw);
-		void *buffs[] = {s->data};
+		memcpy(s->data, rem, rem_n * sizeof(int16_t));
+		void *buffs[] = {s->data + rem_n};
 		int flags = 0; long long t_ns = 0;
-		int r = g_stop ? -1 : SoapySDRDevice_readStream(G.dev, G.stream, buffs, CHUNK_COMPLEX, &flags, &t_ns, 1000000);
+		int r = g_stop ? -1 : SoapySDRDevice_readStream(G.dev, G.stream, buffs, CHUNK_COMPLEX - (rem_n + 1) / 2, &flags, &t_ns, 1000000);
 		if (r == SOAPY_SDR_OVERFLOW) { fprintf(stderr, "O"); fflush(stderr); continue; }      /* :901-905 */
 		if (r <= 0) {
 			if (!g_stop) { fprintf(stderr, "readStream read failed: %d\n", r); }
 			s->n = 0; s->eof = 1; q_end_put(&G.q_raw);
 			break;
 		}
-		size_t n16 = (size_t)r * 2;
-		n16 -= n16 % G.multiple;                       /* librxb200 chunk granularity; a ragged tail is dropped */
-		if (n16 == 0) { continue; }
+		size_t n16 = rem_n + (size_t)r * 2;
+		const size_t over = n16 % G.multiple;           /* librxb200 chunk granularity: the excess opens the next slot */
+		n16 -= over;
+		memcpy(rem, s->data + n16, over * sizeof(int16_t));
+		rem_n = over;
+		if (n16 == 0) { continue; }                      /* less than one granule so far: same slot again */
 		pthread_mutex_lock(&G.hop_m);
 		if (G.mute) {                                  /* zero the first samples after a hop (:839-843) */
 			size_t z = (size_t)G.mute < n16 ? (size_t)G.mute : n16;
@@ -189,7 +198,7 @@ static void *demod_thread(void *arg)
 		size_t n_pcm = 0;
 		int rc = rxb200_fm_process(G.fm, in->data, in->n, in->n, out->data, 2 * CHUNK_COMPLEX, &n_pcm, NULL);
 		q_end_get(&G.q_raw);
-		if (rc != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); g_stop = 1; n_pcm = 0; }
+		if (rc != RXB200_OK) { fprintf(stderr, "rxb200: %s\n", rxb200_last_error()); g_stop = 1; G.failed = 1; n_pcm = 0; }
 		if (G.print_levels && rc == RXB200_OK) {                                  /* :792-806, one chunk per call */
 			int sr = 0; size_t nl = 0;
 			if (rxb200_fm_levels(G.fm, &sr, 1, &nl) == RXB200_OK && nl == 1) {
@@ -208,7 +217,8 @@ static void *demod_thread(void *arg)
 		if (squelch) { rxb200_fm_squelch_hits(G.fm, &hits); }
 		const int squelch_active = squelch && hits > G.conseq_squelch;            /* :928 */
 		if (squelch_active && !G.squelch_zero) {                                  /* :929-933: nothing is written, hop */
-			if (G.terminate_on_squelch) { g_stop = 1; }
+			/* -t <negative> sets terminate_on_squelch in the reference too (:1270-1275), but nothing there ever reads
+			 * it (exit_flag is never set, :925): the stream keeps running, and so does this one */
 			hop_to_next();
 			out->n = 0; out->eof = 0; q_end_put(&G.q_pcm);
 			continue;
@@ -361,5 +371,5 @@ int main(int argc, char **argv)
 	if (G.out != stdout) { fclose(G.out); }
 	rxb200_fm_destroy(G.fm);
 	sdr_close(G.dev, G.stream);
-	return 0;
+	return G.failed ? 1 : 0;
 }

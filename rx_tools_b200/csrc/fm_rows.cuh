@@ -40,10 +40,10 @@ __device__ __forceinline__ void ldg256_row(const int16_t *p, uint32_t *v, uint32
 	             : "l"(p), "r"(dep));
 }
 
-// a lane's 32 samples of one row (128 bytes, one line); `dep` only orders the loads behind its producer
-__device__ __forceinline__ void row_load(const int16_t *in_row, int lane, uint32_t (&v)[ROW_LANE], uint32_t dep)
+// a lane's 32 samples of one row (128 bytes, one line) from p = the lane's first sample; `dep` only orders the loads
+// behind its producer
+__device__ __forceinline__ void row_load(const int16_t *p, uint32_t (&v)[ROW_LANE], uint32_t dep)
 {
-	const int16_t *p = in_row + 2 * ROW_LANE * lane;
 #pragma unroll
 	for (int q = 0; q < ROW_LANE / 8; q++) { ldg256_row(p + 16 * q, &v[8 * q], dep); }
 }
@@ -101,20 +101,29 @@ __device__ __forceinline__ void droop9_words(const int (&c)[6], int fir_bias, ui
 	dq = wrap16(aq >> 15);
 }
 
-// Everything of one row after the scale: x = the lane's 32 samples scaled, rotated and packed (lanes biased by 128).
-// par = parity of the row (which carry slot lane 31 writes); cs = the row starts a chunk; rel = index of the lane's
-// first PCM sample in the item's shared PCM buffer.
-// Returns a word that depends on the row's last results (the caller hangs the next row's prefetched registers on it).
+// One row of one lane.  v: the lane's 32 raw CS16 words (consumed by the scale, then refilled with the NEXT row, whose
+// loads are issued once level 0 is through -- from there on few registers are live, and the rest of the row's work
+// hides the latency).  par = parity of the row (which carry slot lane 31 writes); cs0 = 1 on lane 0 of a chunk's first
+// row; rel = index of the lane's first PCM sample in the item's shared PCM buffer.
+// Returns a word that depends on the row's last results (the caller hangs the prefetched registers on it).
 template <int P, bool FIR>
 __device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int par, int lane, int cs0, bool store,
-                                             const uint32_t (&x)[ROW_LANE], int16_t *pcm_s, int rel)
+                                             uint32_t (&v)[ROW_LANE], const int16_t *next_row, const int16_t *pf_row,
+                                             int16_t *pcm_s, int rel)
 {
 	typedef RowSmem<P> RS;
 	constexpr int NV = RS::NV;
 	uint32_t o[NV];                        // the lane's decimated samples, lanes biased by 128 << P
 	{
 		uint32_t y[ROW_LANE / 2];
-		row_level<ROW_LANE>(xs, RS::CARRY + (0 * 2 + par) * 8, RS::CARRY + (0 * 2 + (par ^ 1)) * 8, lane, cs0, x, y);
+		{
+			uint32_t x[ROW_LANE];
+#pragma unroll
+			for (int j = 0; j < ROW_LANE; j++) { x[j] = scale_rot_pack(v[j], j, true); }
+			row_level<ROW_LANE>(xs, RS::CARRY + (0 * 2 + par) * 8, RS::CARRY + (0 * 2 + (par ^ 1)) * 8, lane, cs0, x, y);
+		}
+		row_load(next_row, v, y[ROW_LANE / 2 - 1]);
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row));      // rows further ahead: into L2, one line per lane
 		if constexpr (P == 1) {
 #pragma unroll
 			for (int j = 0; j < NV; j++) { o[j] = y[j]; }
@@ -199,17 +208,17 @@ __device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, cons
 {
 	typedef RowSmem<P> RS;
 	constexpr int NV = RS::NV;
-	const long long rows_total = k.n / ROW_LEN;
-	const long long own_lo = (long long)it.b * k.n_own;
-	const long long own_hi = own_lo + k.n_own < rows_total ? own_lo + k.n_own : rows_total;
-	const long long buf_lo = own_lo - k.n_extra > 0 ? own_lo - k.n_extra : 0;
-	const int n_rows = (int)(own_hi - buf_lo);
+	// rows fit 32 bits (a call is at most 2^31 samples per channel)
+	const int rows_total = (int)(k.n / ROW_LEN);
+	const int own_lo = it.b * k.n_own;
+	const int own_hi = own_lo + k.n_own < rows_total ? own_lo + k.n_own : rows_total;
+	const int buf_lo = own_lo - k.n_extra > 0 ? own_lo - k.n_extra : 0;
+	const int n_rows = own_hi - buf_lo;
 	const int per = (n_rows + k.fe_warps - 1) / k.fe_warps;
-	const long long r0 = buf_lo + (long long)warp * per;
-	const long long r1 = r0 + per < own_hi ? r0 + per : own_hi;
+	const int r0 = buf_lo + warp * per;
+	const int r1 = r0 + per < own_hi ? r0 + per : own_hi;
 	if (r0 >= r1) { return; }
 	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
-	const int16_t *in = k.in + 2 * (size_t)it.ch * (size_t)k.n;
 	const int rpc = k.chunk / ROW_LEN;              // rows per chunk
 	int par = 0;
 	// what the (non-existent) row before the first one left behind: the call's carry at the start of the stream,
@@ -231,25 +240,26 @@ __device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, cons
 		if (lane == 0) { xs[RS::FPRE + 1] = 0u; }
 	}
 	__syncwarp();
-	long long r = r0 == 0 ? 0 : r0 - 1;             // one replayed row makes every filter exact (the chain remembers 16 << P samples)
+	int r = r0 == 0 ? 0 : r0 - 1;                   // one replayed row makes every filter exact (the chain remembers 16 << P samples)
+	// the lane's sample pointer walks row by row; rows_left counts the loop; to_cs counts down to the next chunk start
+	const int16_t *p = k.in + 2 * ((size_t)it.ch * (size_t)k.n + (size_t)r * ROW_LEN + (size_t)(ROW_LANE * lane));
+	const int16_t *p_last = k.in + 2 * ((size_t)it.ch * (size_t)k.n + (size_t)(rows_total - 1) * ROW_LEN + (size_t)(ROW_LANE * lane));
+	int to_cs = r % rpc;                            // 0: this row starts a chunk
+	int rel = (int)((((long long)r * ROW_LEN) >> P) - it.m_lo) + NV * lane;
+	int skip = r0 - r;                              // rows whose PCM is not stored (the replayed one)
+	int rows_left = r1 - r;
 	uint32_t v[ROW_LANE];
-	row_load(in + 2 * (size_t)r * ROW_LEN, lane, v, 0u);
-	for (; r < r1; r++) {
-		uint32_t x[ROW_LANE];
-#pragma unroll
-		for (int j = 0; j < ROW_LANE; j++) { x[j] = scale_rot_pack(v[j], j, true); }
-		// the raw block's registers are free from here on: the next row is loaded straight into them and has the
-		// rest of this row's work to arrive; the rows after it are pulled into L2 one line per lane
-		const long long rn = r + 1 < r1 ? r + 1 : r;
-		row_load(in + 2 * (size_t)rn * ROW_LEN, lane, v, x[ROW_LANE - 1]);
-		{
-			const long long rp = r + ROW_PF < rows_total ? r + ROW_PF : rows_total - 1;
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2 * (size_t)rp * ROW_LEN + 2 * ROW_LANE * lane));
-		}
-		const int cs0 = ((r % rpc) == 0 && lane == 0) ? k.one : 0;
-		const int rel = (int)(((r * ROW_LEN) >> P) - it.m_lo) + NV * lane;
-		const uint32_t token = row_body<P, FIR>(c, xs, par, lane, cs0, r >= r0, x, pcm_s, rel);
+	row_load(p, v, 0u);
+	for (; rows_left > 0; rows_left--) {
+		const int16_t *pn = rows_left > 1 ? p + 2 * ROW_LEN : p;            // the last row re-reads itself (never used)
+		const int16_t *pf = p + 2 * ROW_LEN * ROW_PF <= p_last ? p + 2 * ROW_LEN * ROW_PF : p_last;
+		const int cs0 = (to_cs == 0 && lane == 0) ? k.one : 0;
+		const uint32_t token = row_body<P, FIR>(c, xs, par, lane, cs0, skip <= 0, v, pn, pf, pcm_s, rel);
 		par ^= 1;
+		p = pn;
+		rel += ROW_LEN >> P;
+		skip--;
+		if (++to_cs == rpc) { to_cs = 0; }
 		// keep the prefetched row in the registers it was loaded into until here: left alone, the compiler copies some
 		// of them right behind the loads and the warp then sits out the whole memory latency
 #pragma unroll
