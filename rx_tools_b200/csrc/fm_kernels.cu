@@ -1328,6 +1328,23 @@ static fm_kernel_fn pick_rows_kernel(int P, int fir_on)
 	}
 #endif
 }
+// the split kernel with the SEGMENT front end: the undecimated wbfm shape (D <= 2 with de-emphasis), where the serial
+// stages are most of the work (62 % of the fused kernel's warp time is spent parked behind them)
+#ifndef SEGS_FE_THREADS
+#define SEGS_FE_THREADS 512
+#endif
+#ifndef SEGS_BE_LANES
+#define SEGS_BE_LANES 128
+#endif
+static fm_kernel_fn pick_segs_kernel(int P, int D, int deemph)
+{
+#ifdef RXB_QUICK
+	return nullptr;
+#else
+	return (P == 0 && D <= 2 && deemph) ? fm_split_kernel<0, 1, 0, SEGS_FE_THREADS + SEGS_BE_LANES, 1> : nullptr;
+#endif
+}
+
 static int rows_xs_words(int P) { return P == 1 ? RowSmem<1>::WORDS : (P == 2 ? RowSmem<2>::WORDS : RowSmem<3>::WORDS); }
 
 static fm_kernel_fn pick_kernel(int P, int spec, int threads)
@@ -1378,9 +1395,12 @@ struct rxb200_fm {
 	rxb200_fm_stats stats;
 	fm_kernel_fn kern;
 	fm_kernel_fn kern_rows;        // split kernel with the row front end (null: shape not covered)
+	fm_kernel_fn kern_segs;        // split kernel with the segment front end (null: shape not covered)
 	int spec;
 	int last_rows;                 // 1: the last process call ran kern_rows
 	int rows_fe_warps, rows_be_lanes;
+	size_t segs_min;               // complex samples per call from which kern_segs is used
+	long long env_seg; int env_be_lanes;   // A/B knobs RXB200_FM_SEG / RXB200_FM_BE_LANES, read once at create
 	int threads;                   // CTA width of kern
 	int wide;                      // all-scalar fifth_order passes (raw DC block on)
 	int smem_optin, smem_per_sm, smem_reserved;
@@ -1470,7 +1490,11 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		h->spec = spec;
 		const int fir_on = (params->downsample_passes > 0 && params->comp_fir_size == 9) ? 1 : 0;
 		h->kern_rows = (spec == 1 && !getenv("RXB200_FM_NOROWS")) ? pick_rows_kernel(params->downsample_passes, fir_on) : nullptr;
+		h->kern_segs = (spec == 1 && !getenv("RXB200_FM_NOSPLIT")) ? pick_segs_kernel(params->downsample_passes, params->downsample, params->deemph) : nullptr;
 		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = ROWS_BE_LANES;
+		h->env_seg = getenv("RXB200_FM_SEG") ? atoll(getenv("RXB200_FM_SEG")) : 0;
+		h->env_be_lanes = getenv("RXB200_FM_BE_LANES") ? atoi(getenv("RXB200_FM_BE_LANES")) : 0;
+		h->segs_min = getenv("RXB200_FM_SEGS_MIN") ? (size_t)atoll(getenv("RXB200_FM_SEGS_MIN")) : (size_t)148 * 32768;
 		{
 			// A/B knobs, read once at create: back-end lanes (32 | 64 ...) of the split kernel
 			const char *e = getenv("RXB200_FM_ROWS_BE");
@@ -1479,27 +1503,29 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 	}
 	if (!h->kern) { set_error("no kernel for downsample_passes %d in this build", params->downsample_passes); delete h->h_lens; delete h; return RXB200_EUNSUPPORTED; }
 	cudaDeviceProp prop;
-	RXB_CUDA(cudaGetDeviceProperties(&prop, device));
+	RXB_CUDA_OR(cudaGetDeviceProperties(&prop, device), rxb200_fm_destroy(h));
 	h->n_sm = prop.multiProcessorCount;
 	h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 	h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
 	h->smem_reserved = (int)prop.reservedSharedMemPerBlock;
-	RXB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-	RXB_CUDA(cudaEventCreate(&h->ev0));
-	RXB_CUDA(cudaEventCreate(&h->ev1));
+	RXB_CUDA_OR(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), rxb200_fm_destroy(h));
+	RXB_CUDA_OR(cudaEventCreate(&h->ev0), rxb200_fm_destroy(h));
+	RXB_CUDA_OR(cudaEventCreate(&h->ev1), rxb200_fm_destroy(h));
 	size_t cbytes = (size_t)n_channels * h->state_words * sizeof(uint32_t);
-	RXB_CUDA(cudaMalloc(&h->d_carry[0], cbytes));
-	RXB_CUDA(cudaMalloc(&h->d_carry[1], cbytes));
+	RXB_CUDA_OR(cudaMalloc(&h->d_carry[0], cbytes), rxb200_fm_destroy(h));
+	RXB_CUDA_OR(cudaMalloc(&h->d_carry[1], cbytes), rxb200_fm_destroy(h));
 	if (params->custom_atan == RXB200_ATAN_LUT && params->mode == RXB200_MODE_FM) {
 		// atan_lut_init (src/rtl_fm.c:515-526): host libm, uploaded once
 		std::vector<int> lut(131072);
 		for (int i = 0; i < 131072; i++) { lut[i] = (int)(atan((double)i / (double)(1 << 8)) / 3.14159 * (double)(1 << 14)); }
-		RXB_CUDA(cudaMalloc(&h->d_atan_lut, lut.size() * sizeof(int)));
-		RXB_CUDA(cudaMemcpy(h->d_atan_lut, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
+		RXB_CUDA_OR(cudaMalloc(&h->d_atan_lut, lut.size() * sizeof(int)), rxb200_fm_destroy(h));
+		RXB_CUDA_OR(cudaMemcpy(h->d_atan_lut, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice), rxb200_fm_destroy(h));
 	}
 	fm_fill_dev(h);
+	rc = rxb200_fm_reset(h);
+	if (rc != RXB200_OK) { rxb200_fm_destroy(h); return rc; }
 	*out = h;
-	return rxb200_fm_reset(h);
+	return RXB200_OK;
 }
 
 extern "C" int rxb200_fm_reset(rxb200_fm *h)
@@ -1529,13 +1555,14 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 {
 	if (!h) { return; }
 	cudaSetDevice(h->device);
-	cudaStreamSynchronize(h->stream);
+	if (h->stream) { cudaStreamSynchronize(h->stream); }
 	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_sync);
 	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
 	cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens); cudaFree(h->d_levels);
 	delete h->h_lens;
-	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-	cudaStreamDestroy(h->stream);
+	if (h->ev0) { cudaEventDestroy(h->ev0); }
+	if (h->ev1) { cudaEventDestroy(h->ev1); }
+	if (h->stream) { cudaStreamDestroy(h->stream); }
 	delete h;
 }
 
@@ -1701,10 +1728,74 @@ static int fm_launch_rows(rxb200_fm *h, const int16_t *d_in, size_t n_int16, siz
 	return RXB200_OK;
 }
 
+// ---- launch of the split kernel with the segment front end: fm_launch's geometry for SEGS_FE_THREADS front-end
+// threads and two PCM buffers, one CTA per SM.
+static int fm_launch_segs(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t chunk_int16, int16_t *d_out, size_t out_stride)
+{
+	const rxb200_fm_params &p = h->p;
+	const FmDev &dv = h->dev;
+	const long long n = (long long)(n_int16 / 2);
+	const int T = SEGS_FE_THREADS, be_lanes = SEGS_BE_LANES;
+	const long long D = dv.D, G = 8;
+	const long long halo = round_up_ll(3 * D, G);
+	const long long W_dec = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64;
+	const long long margin_dec = W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
+	cudaFuncAttributes fa;
+	RXB_CUDA(cudaFuncGetAttributes(&fa, h->kern_segs));
+	const long long dyn_max = (long long)h->smem_optin - (long long)fa.sharedSizeBytes;
+	long long Sf = 0, n_extra = 0, pcm_cap = 0;
+	for (long long sf = h->tune_seg > 0 ? round_up_ll(h->tune_seg, G) : 4096; sf >= G; sf -= G) {
+		long long ne = (margin_dec * D + halo + sf - 1) / sf;
+		long long cap = (long long)T * (sf / D + 2) + 64;
+		cap += PCM_PAD_SEG * (cap >> 7) + 8;
+		cap = (cap + 7) & ~7LL;
+		if (2 * cap * (long long)sizeof(int16_t) <= dyn_max && ne <= T / 2) { Sf = sf; n_extra = ne; pcm_cap = cap; break; }
+	}
+	if (Sf == 0) { set_error("no segment length fits the split kernel's PCM buffers (replay %lld samples)", margin_dec * D); return RXB200_EUNSUPPORTED; }
+	const long long n_own = T - n_extra;
+	const long long n_cta = (n + n_own * Sf - 1) / (n_own * Sf);
+	const size_t smem = 2 * (size_t)pcm_cap * sizeof(int16_t);
+	RXB_CUDA(cudaFuncSetAttribute(h->kern_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern_segs, T + be_lanes, smem));
+	if (per_sm < 1) { set_error("split kernel does not fit an SM (%zu bytes of shared memory)", smem); return RXB200_EUNSUPPORTED; }
+	const size_t total_work = (size_t)n_cta * h->n_channels;
+	const size_t need_sync = 4 + 4 * total_work;
+	if (need_sync > h->sync_cap) {
+		cudaFree(h->d_sync); h->d_sync = nullptr; h->sync_cap = 0;
+		RXB_CUDA(cudaMalloc(&h->d_sync, need_sync * sizeof(int)));
+		h->sync_cap = need_sync;
+	}
+	FmCall k;
+	memset(&k, 0, sizeof k);
+	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
+	k.n_ch = h->n_channels; k.Sf = (int)Sf; k.halo = (int)halo; k.n_extra = (int)n_extra; k.n_own = (int)n_own;
+	k.n_cta = (int)n_cta; k.W_dec = (int)W_dec; k.pcm_cap = (int)pcm_cap; k.direct_out = 0;
+	k.be_lanes = be_lanes; k.fe_threads = T; k.fe_warps = T / 32; k.xs_words = 0;
+	k.state_words = h->state_words; k.carry_in = h->d_carry[h->cur]; k.carry_out = h->d_carry[h->cur ^ 1];
+	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
+	k.n_chunks = (int)((n + k.chunk - 1) / k.chunk);
+	k.reduce_mode = 0; k.one = 1;
+	size_t blocks = (size_t)h->n_sm * per_sm;
+	if (blocks > total_work) { blocks = total_work; }
+	RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
+	RXB_CUDA(cudaEventRecord(h->ev0, h->stream));
+	h->kern_segs<<<(unsigned)blocks, T + be_lanes, smem, h->stream>>>(dv, k);
+	RXB_CUDA(cudaGetLastError());
+	RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
+	h->cur ^= 1;
+	h->last_rows = 1;
+	h->stats.launches = 1; h->stats.segments = (int)(total_work * T); h->stats.segment_len = (int)Sf;
+	h->stats.warmup_len = (int)(W_dec * D); h->stats.fixup_segments = -1; h->stats.kernel_kind = 2;
+	return RXB200_OK;
+}
+
 static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t chunk_int16, int16_t *d_out,
                      size_t out_stride)
 {
 	if (fm_rows_shape_ok(h, n_int16, chunk_int16)) { return fm_launch_rows(h, d_in, n_int16, chunk_int16, d_out, out_stride); }
+	// the split kernel pays off once there are a few items per SM; short calls (streaming chunks) stay on the fused kernel
+	if (h->kern_segs && n_int16 / 2 >= h->segs_min) { return fm_launch_segs(h, d_in, n_int16, chunk_int16, d_out, out_stride); }
 	h->last_rows = 0;
 	const rxb200_fm_params &p = h->p;
 	const FmDev &dv = h->dev;
@@ -1726,14 +1817,27 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const long long margin_dec = direct_out ? 0 : W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
 	// segment per thread: ~128 decimated samples, at least 4 halos, capped so the PCM buffer stays small
 	long long Sf = h->tune_seg;
-	if (Sf <= 0) { const char *e = getenv("RXB200_FM_SEG"); Sf = e ? atoll(e) : 0; }
+	if (Sf <= 0) { Sf = h->env_seg; }
 	if (Sf <= 0) {
 		Sf = 128 * Dpcm;
 		if (Sf > 2048) { Sf = 2048; }
 		if (Sf < 4 * halo) { Sf = 4 * halo; }
 	}
+	// Boxcar shapes: a segment that is a whole number of boxcar periods (and of 8-sample blocks) starts every thread
+	// of a warp at the same decimation phase, so all lanes emit their decimated sample in the same iteration.  With
+	// other lengths the lanes emit in different iterations and the discriminator / LUT / store code runs once per
+	// phase instead of once per period: measured on fm5a (D = 100) 0.35 ms at multiples of 200 against 0.80 ms
+	// (profiles/r2_seg_sweep/).  Gs = lcm(D, 8) when that still leaves a sensible segment.
+	long long Gs = G;
+	if (P == 0) {
+		long long a = Dpcm, b = 8;
+		while (b) { long long t = a % b; a = b; b = t; }
+		const long long l = Dpcm / a * 8;
+		if (l <= 1024) { Gs = l; }
+	}
+	if (h->tune_seg <= 0 && h->env_seg <= 0 && Sf >= 2 * Gs) { Sf = (Sf / Gs) * Gs; }
 	Sf = round_up_ll(Sf, G);
-	const bool sf_forced = (h->tune_seg > 0) || getenv("RXB200_FM_SEG");
+	const bool sf_forced = (h->tune_seg > 0) || (h->env_seg > 0);
 	long long n_extra = 0, n_own = 0, stretch = 0, n_cta = 0, ppt = 0, pcm_cap = 0;
 	size_t smem = 0;
 	auto geometry = [&](long long sf) -> bool {
@@ -1770,7 +1874,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		const double slots = (double)h->n_sm * per_sm;
 		long long best = Sf;
 		double best_cost = 1e30;
-		for (long long sf = Sf; sf >= G && sf * 10 >= Sf * 6; sf -= G) {
+		for (long long sf = Sf; sf >= Gs && sf * 10 >= Sf * 6; sf -= Gs) {
 			if (!geometry(sf)) { continue; }
 			double waves = (double)(n_cta * h->n_channels) / slots;
 			double cost = (waves <= 1.0 ? 1.0 : ceil(waves) / waves) * (1.0 + (double)halo / (double)sf) *
@@ -1796,10 +1900,10 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	{
 		// back-end width: enough lanes that a piece is about half a replay long (more lanes shorten the
 		// phase in which the other warps idle, but every lane pays the full replay)
-		const char *e = getenv("RXB200_FM_BE_LANES");
+		const char *e = h->env_be_lanes > 0 ? "x" : nullptr;
 		const long long item_pcm = n_own * Sf / Dpcm;
 		long long want = W_dec > 0 ? (2 * item_pcm / W_dec + 31) / 32 * 32 : 128;
-		int bl = e ? atoi(e) : (int)want;
+		int bl = e ? h->env_be_lanes : (int)want;
 		bl = (bl / 32) * 32;
 		if (bl < 32) { bl = 32; }
 		if (bl > T) { bl = T; }

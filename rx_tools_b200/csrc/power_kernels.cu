@@ -599,6 +599,7 @@ struct rxb200_power {
 	cudaEvent_t ev0, ev1;
 	void *d_db = nullptr; size_t db_cap = 0;   // csv_dbm staging (rxb200_power_read_db)
 	int triv = 0;                              // see PowArgs::triv
+	int force_v1 = 0;                          // RXB200_POWER_V1 (A/B knob, read once at create): generic kernel only
 };
 
 static int power_validate(const rxb200_power_params *p)
@@ -646,6 +647,7 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 	h->p = *params; h->device = device; h->d_avg = nullptr; h->d_samples = nullptr; h->d_sine = nullptr; h->d_window = nullptr;
 	h->d_in = nullptr; h->d_in_cap = 0; h->launches = 0;
 	h->samples.assign(params->n_hops, 0);
+	h->force_v1 = getenv("RXB200_POWER_V1") ? 1 : 0;
 	cudaDeviceProp prop;
 	RXB_CUDA_OR(cudaGetDeviceProperties(&prop, device), rxb200_power_destroy(h));
 	h->n_sm = prop.multiProcessorCount;
@@ -763,7 +765,7 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		a.tables_in_smem = 1;
 		if (smem > 227 * 1024) { smem = 16 + 256 + (size_t)h->p.buf_len * 2; a.tables_in_smem = 0; }
 		cudaError_t e;
-		const bool fast = (h->p.downsample == 1 && h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !getenv("RXB200_POWER_V1"));
+		const bool fast = (h->p.downsample == 1 && h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !h->force_v1);
 		if (fast) {
 			// one CTA of 1024 threads per (hop, pass-slice); ~1 CTA per SM resident
 			int sl = (h->n_sm + nh - 1) / nh;

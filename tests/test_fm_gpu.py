@@ -185,3 +185,34 @@ def test_levels(case, port):
     with pytest.raises(_lib.Rxb200Error):
         d2.levels()
     d2.close()
+
+
+@pytest.mark.parametrize("seg", [0, 32, 64])
+@pytest.mark.parametrize("name", ["cfg2A", "zeros_deemph"])
+def test_split_kernel_with_segment_front_end(name, seg, port, monkeypatch):
+    """The undecimated wbfm shape on long calls runs the split kernel with per-thread segments (front-end threads and
+    back-end warps on different items, two PCM buffers).  RXB200_FM_SEGS_MIN=0 selects it for a test-sized call."""
+    monkeypatch.setenv("RXB200_FM_SEGS_MIN", "0")
+    case = next(c for c in fm_cases() if c.name == name)
+    x = case.make_input()
+    want = port.fm_run(case.params, x, case.chunk_int16)
+    d = fm.FmDemod(case.params)
+    if seg:
+        d.tune(segment_len=seg)
+    got = d.full_demod(x, case.chunk_int16)
+    _compare(case, got, want)
+    assert d.stats()["kernel_kind"] == 2
+    # streaming: the carry written by the split kernel feeds the next call
+    d.reset()
+    cut = (x.size // 3 // case.chunk_int16) * case.chunk_int16 or case.chunk_int16
+    got2 = np.concatenate([d.full_demod(x[:cut], case.chunk_int16), d.full_demod(x[cut:], case.chunk_int16)])
+    _compare(case, got2, want)
+    d.close()
+
+
+def test_row_kernel_is_the_one_that_runs(port):
+    case = next(c for c in fm_cases() if c.name == "cfg2B")
+    d = fm.FmDemod(case.params)
+    d.full_demod(case.make_input(), case.chunk_int16)
+    assert d.stats()["kernel_kind"] == 1 and d.stats()["kernel"] == "fm_split_kernel"
+    d.close()
