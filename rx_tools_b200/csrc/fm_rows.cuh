@@ -50,9 +50,9 @@ __device__ __forceinline__ void row_load(const int16_t *p, uint32_t (&v)[ROW_LAN
 
 // hand the level's tail (its last six inputs, oldest first) to the next lane and fetch the five inputs before this
 // lane's block.  cs0: lane 0 of a chunk's first row -- the pass forgot its pending odd sample, the history is one older.
-// cs_trip: 1 on lane 0 of a chunk's first row, else 0 -- the trip count of a loop, so that the rare case is a branch
-// and not five predicated moves in every row.
-__device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carry_r, int lane, int cs_trip,
+// CS: the row starts a chunk (a separate instantiation of the whole row, so the common rows carry none of this).
+template <bool CS>
+__device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carry_r, int lane,
                                              uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
                                              uint32_t (&h)[5])
 {
@@ -67,18 +67,17 @@ __device__ __forceinline__ void row_exchange(uint32_t *xs, int carry_w, int carr
 	const uint4 a = *reinterpret_cast<const uint4 *>(rq);
 	const uint2 b = *reinterpret_cast<const uint2 *>(rd);
 	h[0] = a.y; h[1] = a.z; h[2] = a.w; h[3] = b.x; h[4] = b.y;
-#pragma unroll 1
-	for (int z = 0; z < cs_trip; z++) { h[4] = b.x; h[3] = a.w; h[2] = a.z; h[1] = a.y; h[0] = a.x; }
+	if (CS && lane == 0) { h[4] = b.x; h[3] = a.w; h[2] = a.z; h[1] = a.y; h[0] = a.x; }
 }
 
 // one fifth_order pass over the lane's M inputs -> M/2 outputs (src/rtl_fm.c:411-440); output j is the tap set over
 // inputs 2j-5 .. 2j of the level's sequence
-template <int M>
-__device__ __forceinline__ void row_level(uint32_t *xs, int carry_w, int carry_r, int lane, int cs0,
+template <int M, bool CS>
+__device__ __forceinline__ void row_level(uint32_t *xs, int carry_w, int carry_r, int lane,
                                           const uint32_t (&in)[M], uint32_t (&out)[M / 2])
 {
 	uint32_t h[5];
-	row_exchange(xs, carry_w, carry_r, lane, cs0, in[M - 6], in[M - 5], in[M - 4], in[M - 3], in[M - 2], in[M - 1], h);
+	row_exchange<CS>(xs, carry_w, carry_r, lane, in[M - 6], in[M - 5], in[M - 4], in[M - 3], in[M - 2], in[M - 1], h);
 	out[0] = hb_tap(h[0], h[1], h[2], h[3], h[4], in[0]);
 	out[1] = hb_tap(h[2], h[3], h[4], in[0], in[1], in[2]);
 	out[2] = hb_tap(h[4], in[0], in[1], in[2], in[3], in[4]);
@@ -103,11 +102,11 @@ __device__ __forceinline__ void droop9_words(const int (&c)[6], int fir_bias, ui
 
 // One row of one lane.  v: the lane's 32 raw CS16 words (consumed by the scale, then refilled with the NEXT row, whose
 // loads are issued once level 0 is through -- from there on few registers are live, and the rest of the row's work
-// hides the latency).  par = parity of the row (which carry slot lane 31 writes); cs0 = 1 on lane 0 of a chunk's first
-// row; rel = index of the lane's first PCM sample in the item's shared PCM buffer.
+// hides the latency).  par = parity of the row (which carry slot lane 31 writes); CS = the row starts a chunk;
+// rel = index of the lane's first PCM sample in the item's shared PCM buffer.
 // Returns a word that depends on the row's last results (the caller hangs the prefetched registers on it).
-template <int P, bool FIR>
-__device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int par, int lane, int cs0, bool store,
+template <int P, bool FIR, bool CS>
+__device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int par, int lane, bool store,
                                              uint32_t (&v)[ROW_LANE], const int16_t *next_row, const int16_t *pf_row,
                                              int16_t *pcm_s, int rel)
 {
@@ -120,7 +119,7 @@ __device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int p
 			uint32_t x[ROW_LANE];
 #pragma unroll
 			for (int j = 0; j < ROW_LANE; j++) { x[j] = scale_rot_pack(v[j], j, true); }
-			row_level<ROW_LANE>(xs, RS::CARRY + (0 * 2 + par) * 8, RS::CARRY + (0 * 2 + (par ^ 1)) * 8, lane, cs0, x, y);
+			row_level<ROW_LANE, CS>(xs, RS::CARRY + (0 * 2 + par) * 8, RS::CARRY + (0 * 2 + (par ^ 1)) * 8, lane, x, y);
 		}
 		row_load(next_row, v, y[ROW_LANE / 2 - 1]);
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row));      // rows further ahead: into L2, one line per lane
@@ -129,12 +128,12 @@ __device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int p
 			for (int j = 0; j < NV; j++) { o[j] = y[j]; }
 		} else {
 			uint32_t z[ROW_LANE / 4];
-			row_level<ROW_LANE / 2>(xs, RS::CARRY + (1 * 2 + par) * 8, RS::CARRY + (1 * 2 + (par ^ 1)) * 8, lane, cs0, y, z);
+			row_level<ROW_LANE / 2, CS>(xs, RS::CARRY + (1 * 2 + par) * 8, RS::CARRY + (1 * 2 + (par ^ 1)) * 8, lane, y, z);
 			if constexpr (P == 2) {
 #pragma unroll
 				for (int j = 0; j < NV; j++) { o[j] = z[j]; }
 			} else {
-				row_level<ROW_LANE / 4>(xs, RS::CARRY + (2 * 2 + par) * 8, RS::CARRY + (2 * 2 + (par ^ 1)) * 8, lane, cs0, z, o);
+				row_level<ROW_LANE / 4, CS>(xs, RS::CARRY + (2 * 2 + par) * 8, RS::CARRY + (2 * 2 + (par ^ 1)) * 8, lane, z, o);
 			}
 		}
 	}
@@ -182,10 +181,7 @@ __device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int p
 		const int cr = add_w(mul_w(di[j], br), mul_w(dq[j], bj));
 		const int cj = sub_w(mul_w(dq[j], br), mul_w(di[j], bj));
 		pcm[j] = fast_atan2_i(cj, cr);
-		if (j == 0) {
-#pragma unroll 1
-			for (int z = 0; z < cs0; z++) { pcm[0] = disc_std(cr, cj); }      // F8: the first sample of a chunk goes through atan2
-		}
+		if (CS && j == 0 && lane == 0) { pcm[0] = disc_std(cr, cj); }       // F8: the first sample of a chunk goes through atan2
 		br = di[j]; bj = dq[j];
 	}
 	if (store) {
@@ -253,8 +249,10 @@ __device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, cons
 	for (; rows_left > 0; rows_left--) {
 		const int16_t *pn = rows_left > 1 ? p + 2 * ROW_LEN : p;            // the last row re-reads itself (never used)
 		const int16_t *pf = p + 2 * ROW_LEN * ROW_PF <= p_last ? p + 2 * ROW_LEN * ROW_PF : p_last;
-		const int cs0 = (to_cs == 0 && lane == 0) ? k.one : 0;
-		const uint32_t token = row_body<P, FIR>(c, xs, par, lane, cs0, skip <= 0, v, pn, pf, pcm_s, rel);
+		// a chunk's first row is its own instantiation (warp-uniform branch): the common rows carry no trace of it
+		uint32_t token;
+		if (to_cs == 0) { token = row_body<P, FIR, true>(c, xs, par, lane, skip <= 0, v, pn, pf, pcm_s, rel); }
+		else { token = row_body<P, FIR, false>(c, xs, par, lane, skip <= 0, v, pn, pf, pcm_s, rel); }
 		par ^= 1;
 		p = pn;
 		rel += ROW_LEN >> P;
@@ -262,11 +260,15 @@ __device__ __forceinline__ void front_rows(const FmDev &c, const FmCall &k, cons
 		if (++to_cs == rpc) { to_cs = 0; }
 		// keep the prefetched row in the registers it was loaded into until here: left alone, the compiler copies some
 		// of them right behind the loads and the warp then sits out the whole memory latency
+#ifndef ROW_NO_FENCE
 #pragma unroll
 		for (int q = 0; q < ROW_LANE; q += 8) {
 			asm volatile("" : "+r"(v[q]), "+r"(v[q + 1]), "+r"(v[q + 2]), "+r"(v[q + 3]), "+r"(v[q + 4]), "+r"(v[q + 5]), "+r"(v[q + 6]), "+r"(v[q + 7])
 			             : "r"(token));
 		}
+#else
+		(void)token;
+#endif
 	}
 	if (r1 == rows_total) {
 		// this warp saw the end of the stream: lane 31's tails are the next call's carry (same layout as front_store)

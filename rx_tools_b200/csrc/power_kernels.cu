@@ -399,14 +399,20 @@ __device__ __forceinline__ void trip_first_triv(Cx (&x)[8], const uint32_t *tw)
 	bfly(x[6], x[7], wr, wi);
 }
 
-template <int E>
-__global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
+// T = threads per CTA.  1024: one thread per eight points of the hop buffer, one CTA per SM.  512: two CTAs per SM, each
+// walking its hop buffer in two halves (upper half of the N-blocks first, see the layout note below) -- the barriers,
+// the TMA wait and the DC reduction of one CTA hide behind the butterflies of the other.  A thread meets the same
+// eight bins in both halves, so the accumulators are shared.
+template <int E, int T>
+__global__ void __launch_bounds__(T, 1024 / T) power_fft8_kernel(const PowArgs a)
 {
 	constexpr int N = 1 << E;
 	constexpr int UPB = N / 8;                 // threads per N-block
 	constexpr int NT = (E + 2) / 3;            // trips through shared memory
 	constexpr int REM = E % 3;                 // stages in the last trip when not a multiple of 3
 	constexpr int BUFW = 8192 + 1024;          // words per hop buffer incl. padding
+	constexpr int NH = 1024 / T;               // halves of the hop buffer a CTA walks through
+	static_assert(UPB <= T, "an N-block's threads must sit in one half");
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);                   // two mbarriers
 	long long *red = reinterpret_cast<long long *>(smem_raw + 16);            // 64 x 8 B
@@ -417,16 +423,15 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 	const int hop_local = blockIdx.x / a.slices;
 	const int slice = blockIdx.x % a.slices;
 	const int hop = a.hop_begin + hop_local;
-	const int blk = tid >> (E - 3);
-	const int uu = tid & (UPB - 1);
+	const int uu = tid & (UPB - 1);            // the same in every half (UPB divides T)
 
 	// tables: packed twiddles (wr = Sinewave[j + N/4] >> 1, wi = (-Sinewave[j]) >> 1, src/rtl_power.c:298-301)
-	for (int i = tid; i < N / 2; i += 1024) {
+	for (int i = tid; i < N / 2; i += T) {
 		int wr = (int)a.sine[i + N / 4] >> 1;
 		int wi = (-(int)a.sine[i]) >> 1;
 		tw[i] = ppack(wr, wi);
 	}
-	for (int i = tid; i < N; i += 1024) { win[i] = a.window[i]; }
+	for (int i = tid; i < N; i += T) { win[i] = a.window[i]; }
 	if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
 	__syncthreads();
 
@@ -453,69 +458,80 @@ __global__ void __launch_bounds__(1024, 1) power_fft8_kernel(const PowArgs a)
 			mbar_expect_tx(&bar[cur ^ 1], 32768u);
 			bulk_load(bufs + (cur ^ 1) * BUFW, src0 + (size_t)(pass + a.slices) * hop_stride, 32768u, &bar[cur ^ 1]);
 		}
-		// ---- trip 0 loads: n = j*N/8 + uu of block blk, straight from the TMA image
-		uint32_t raw[8];
+		// remove_dc over the whole hop buffer (src/rtl_power.c:609-624, :744-745): every thread sums the points it
+		// will transform, straight from the TMA image
 		long long si = 0, sq = 0;
 #pragma unroll
-		for (int j = 0; j < 8; j++) {
-			raw[j] = buf[blk * N + j * UPB + uu];
-			si += plo(raw[j]); sq += phi(raw[j]);
+		for (int hf = 0; hf < NH; hf++) {
+			const int blk = (tid + hf * T) >> (E - 3);
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const uint32_t w = buf[blk * N + j * UPB + uu];
+				si += plo(w); sq += phi(w);
+			}
 		}
-		// remove_dc over the whole hop buffer (src/rtl_power.c:609-624, :744-745)
 		for (int o = 16; o > 0; o >>= 1) { si += __shfl_down_sync(0xffffffffu, si, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
 		if ((tid & 31) == 0) { red[tid >> 5] = si; red[32 + (tid >> 5)] = sq; }
 		__syncthreads();
 		long long ti_ = 0, tq_ = 0;
 #pragma unroll 8
-		for (int w = 0; w < 32; w++) { ti_ += red[w]; tq_ += red[32 + w]; }
+		for (int w = 0; w < T / 32; w++) { ti_ += red[w]; tq_ += red[32 + w]; }
 		const int ave_i = (int)(int16_t)(ti_ / 16384LL);
 		const int ave_q = (int)(int16_t)(tq_ / 16383LL);
-		Cx x[8];
+		// Layout note: trip t > 0 keeps block b at b * (N + UPB) (padded), the TMA image has it at b * N.  The padded
+		// region of the upper half of the blocks starts past the raw image of the lower half, so the upper half goes
+		// first and the lower half's raw samples are still intact when their turn comes.
 #pragma unroll
-		for (int j = 0; j < 8; j++) {      // window multiply with int16 wrap (:749-758)
-			const int w = win[j * UPB + uu];
-			x[j].re = (plo(raw[j]) - ave_i) * w;          // low 16 bits = the reference's int16 store
-			x[j].im = (phi(raw[j]) - ave_q) * w;
-		}
+		for (int hf = NH - 1; hf >= 0; hf--) {
+			const int blk = (tid + hf * T) >> (E - 3);
+			Cx x[8];
 #pragma unroll
-		for (int t = 0; t < NT; t++) {
-			const bool last = (t == NT - 1);
-			// geometry of this trip: stages s0, s0+1, s0+2 (the last trip of a non-multiple-of-3 E re-uses
-			// s0 = E-3 and skips the stages an earlier trip already did)
-			const int s0 = (last && REM != 0) ? (E - 3) : 3 * t;
-			const int first = (last && REM != 0) ? (3 - REM) : 0;
-			const int lbw = E - 3 - s0;               // log2 of the spacing of the thread's points
-			const int B = uu & ((1 << lbw) - 1);
-			const int A = uu >> lbw;
-			if (t > 0) {
+			for (int j = 0; j < 8; j++) {      // trip 0 loads: n = j*N/8 + uu of block blk; window multiply with int16 wrap (:749-758)
+				const uint32_t raw = buf[blk * N + j * UPB + uu];
+				const int w = win[j * UPB + uu];
+				x[j].re = (plo(raw) - ave_i) * w;             // low 16 bits = the reference's int16 store
+				x[j].im = (phi(raw) - ave_q) * w;
+			}
 #pragma unroll
-				for (int j = 0; j < 8; j++) {
-					uint32_t w = buf[blk * (N + UPB) + A * (9 << lbw) + (j << lbw) + B];
-					x[j].re = plo(w); x[j].im = phi(w);
+			for (int t = 0; t < NT; t++) {
+				const bool last = (t == NT - 1);
+				// geometry of this trip: stages s0, s0+1, s0+2 (the last trip of a non-multiple-of-3 E re-uses
+				// s0 = E-3 and skips the stages an earlier trip already did)
+				const int s0 = (last && REM != 0) ? (E - 3) : 3 * t;
+				const int first = (last && REM != 0) ? (3 - REM) : 0;
+				const int lbw = E - 3 - s0;               // log2 of the spacing of the thread's points
+				const int B = uu & ((1 << lbw) - 1);
+				const int A = uu >> lbw;
+				if (t > 0) {
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						uint32_t w = buf[blk * (N + UPB) + A * (9 << lbw) + (j << lbw) + B];
+						x[j].re = plo(w); x[j].im = phi(w);
+					}
+				}
+				const int rA = s0 > 0 ? (int)(__brev((unsigned)A) >> (32 - (s0 > 0 ? s0 : 1))) : 0;
+				if (t == 0 && first == 0 && a.triv) { trip_first_triv<E>(x, tw); }
+				else { trip_stages<E>(x, tw, rA, s0, first); }
+				if (!last) {
+					// store in the layout of the next trip: slot n -> n + (n >> (lbw' + 3)) << lbw'
+					const int s0n = (t + 1 == NT - 1 && REM != 0) ? (E - 3) : 3 * (t + 1);
+					const int lbn = E - 3 - s0n;
+					__syncthreads();               // all loads of this trip are done: the buffer may be rewritten in place
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						const int n = (A << (lbw + 3)) + (j << lbw) + B;
+						buf[blk * (N + UPB) + n + ((n >> (lbn + 3)) << lbn)] = ppack(x[j].re, x[j].im);
+					}
+					__syncthreads();
 				}
 			}
-			const int rA = s0 > 0 ? (int)(__brev((unsigned)A) >> (32 - (s0 > 0 ? s0 : 1))) : 0;
-			if (t == 0 && first == 0 && a.triv) { trip_first_triv<E>(x, tw); }
-			else { trip_stages<E>(x, tw, rA, s0, first); }
-			if (!last) {
-				// store in the layout of the next trip: slot n -> n + (n >> (lbw' + 3)) << lbw'
-				const int s0n = (t + 1 == NT - 1 && REM != 0) ? (E - 3) : 3 * (t + 1);
-				const int lbn = E - 3 - s0n;
-				__syncthreads();               // all loads of this trip are done: the buffer may be rewritten in place
+			// real_conj accumulate (:664-668, :760-768): this thread's slots are n = 8*uu + j
 #pragma unroll
-				for (int j = 0; j < 8; j++) {
-					const int n = (A << (lbw + 3)) + (j << lbw) + B;
-					buf[blk * (N + UPB) + n + ((n >> (lbn + 3)) << lbn)] = ppack(x[j].re, x[j].im);
-				}
-				__syncthreads();
+			for (int j = 0; j < 8; j++) {
+				const int vr = (int)(int16_t)x[j].re, vi = (int)(int16_t)x[j].im;      // the reference's int16 store
+				const long long pw = (long long)((unsigned)(vr * vr) + (unsigned)(vi * vi));   // <= 2^31: fits 32 bits unsigned
+				if (a.peak_hold) { acc[j] = pw > acc[j] ? pw : acc[j]; } else { acc[j] += pw; }
 			}
-		}
-		// real_conj accumulate (:664-668, :760-768): this thread's slots are n = 8*uu + j
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const int vr = (int)(int16_t)x[j].re, vi = (int)(int16_t)x[j].im;      // the reference's int16 store
-			const long long pw = (long long)((unsigned)(vr * vr) + (unsigned)(vi * vi));   // <= 2^31: fits 32 bits unsigned
-			if (a.peak_hold) { acc[j] = pw > acc[j] ? pw : acc[j]; } else { acc[j] += pw; }
 		}
 	}
 	// slot n of a block holds bin rev(n)
@@ -600,6 +616,7 @@ struct rxb200_power {
 	void *d_db = nullptr; size_t db_cap = 0;   // csv_dbm staging (rxb200_power_read_db)
 	int triv = 0;                              // see PowArgs::triv
 	int force_v1 = 0;                          // RXB200_POWER_V1 (A/B knob, read once at create): generic kernel only
+	int fft8_threads = 0;                      // RXB200_POWER_THREADS = 512 | 1024 (A/B knob): CTA width of the fast path
 };
 
 static int power_validate(const rxb200_power_params *p)
@@ -648,6 +665,7 @@ extern "C" int rxb200_power_create(const rxb200_power_params *params, const int 
 	h->d_in = nullptr; h->d_in_cap = 0; h->launches = 0;
 	h->samples.assign(params->n_hops, 0);
 	h->force_v1 = getenv("RXB200_POWER_V1") ? 1 : 0;
+	h->fft8_threads = getenv("RXB200_POWER_THREADS") ? atoi(getenv("RXB200_POWER_THREADS")) : 0;
 	cudaDeviceProp prop;
 	RXB_CUDA_OR(cudaGetDeviceProperties(&prop, device), rxb200_power_destroy(h));
 	h->n_sm = prop.multiProcessorCount;
@@ -706,30 +724,26 @@ static cudaError_t launch_fft(const PowArgs &a, int blocks, size_t smem, cudaStr
 	return cudaGetLastError();
 }
 
-template <int E>
+template <int E, int T>
 static cudaError_t launch_fft8_e(const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
 {
-	cudaError_t e = cudaFuncSetAttribute(power_fft8_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(power_fft8_kernel<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) { return e; }
-	power_fft8_kernel<E><<<blocks, 1024, smem, st>>>(a);
+	power_fft8_kernel<E, T><<<blocks, T, smem, st>>>(a);
 	return cudaGetLastError();
 }
-static cudaError_t launch_fft8(int bin_e, const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
+// threads per CTA of the fast path: 512 (two CTAs per SM) wherever an N-block fits half a CTA, i.e. up to N = 4096
+static int fft8_threads(int bin_e, int force) { return (force == 512 || force == 1024) ? (bin_e <= 12 ? force : 1024) : (bin_e <= 12 ? 512 : 1024); }
+static cudaError_t launch_fft8(int bin_e, int threads, const PowArgs &a, int blocks, size_t smem, cudaStream_t st)
 {
+#define RXB_FFT8_CASE(E) case E: return threads == 512 ? launch_fft8_e<E, 512>(a, blocks, smem, st) : launch_fft8_e<E, 1024>(a, blocks, smem, st);
 	switch (bin_e) {
-	case 3: return launch_fft8_e<3>(a, blocks, smem, st);
-	case 4: return launch_fft8_e<4>(a, blocks, smem, st);
-	case 5: return launch_fft8_e<5>(a, blocks, smem, st);
-	case 6: return launch_fft8_e<6>(a, blocks, smem, st);
-	case 7: return launch_fft8_e<7>(a, blocks, smem, st);
-	case 8: return launch_fft8_e<8>(a, blocks, smem, st);
-	case 9: return launch_fft8_e<9>(a, blocks, smem, st);
-	case 10: return launch_fft8_e<10>(a, blocks, smem, st);
-	case 11: return launch_fft8_e<11>(a, blocks, smem, st);
-	case 12: return launch_fft8_e<12>(a, blocks, smem, st);
-	case 13: return launch_fft8_e<13>(a, blocks, smem, st);
+	RXB_FFT8_CASE(3) RXB_FFT8_CASE(4) RXB_FFT8_CASE(5) RXB_FFT8_CASE(6) RXB_FFT8_CASE(7) RXB_FFT8_CASE(8)
+	RXB_FFT8_CASE(9) RXB_FFT8_CASE(10) RXB_FFT8_CASE(11) RXB_FFT8_CASE(12)
+	case 13: return launch_fft8_e<13, 1024>(a, blocks, smem, st);
 	default: return cudaErrorInvalidValue;
 	}
+#undef RXB_FFT8_CASE
 }
 
 extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_hop_bufs, int n_pass,
@@ -767,13 +781,14 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		cudaError_t e;
 		const bool fast = (h->p.downsample == 1 && h->p.buf_len == 16384 && h->p.bin_e >= 3 && h->p.bin_e <= 13 && !h->force_v1);
 		if (fast) {
-			// one CTA of 1024 threads per (hop, pass-slice); ~1 CTA per SM resident
-			int sl = (h->n_sm + nh - 1) / nh;
+			// one CTA per (hop, pass-slice); 1024 threads: ~1 CTA per SM resident, 512 threads: 2
+			const int threads = fft8_threads(h->p.bin_e, h->fft8_threads);
+			int sl = (h->n_sm * (1024 / threads) + nh - 1) / nh;
 			if (sl > n_pass) { sl = n_pass; }
 			if (sl < 1) { sl = 1; }
 			a.slices = sl;
 			const size_t sm8 = 16 + 512 + 2 * (8192 + 1024) * 4 + (size_t)(N / 2 > 4 ? N / 2 : 4) * 4 + (size_t)N * 2;
-			e = launch_fft8(h->p.bin_e, a, nh * sl, sm8, h->stream);
+			e = launch_fft8(h->p.bin_e, threads, a, nh * sl, sm8, h->stream);
 			if (e != cudaSuccess) { set_error("power_fft8_kernel launch: %s", cudaGetErrorString(e)); return RXB200_ECUDA; }
 		} else {
 		const int nb = N / 256;
