@@ -28,8 +28,11 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True)
-    rows = list(csv.reader(io.StringIO(out.stdout)))
+    if path.endswith(".csv"):                 # the raw page already exported on the GPU box (ncu -i ... --page raw --csv)
+        rows = list(csv.reader(open(path)))
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True)
+        rows = list(csv.reader(io.StringIO(out.stdout)))
     names, units = rows[0], rows[1]
     for vals in rows[2:]:
         rec = dict(zip(names, zip(units, vals)))

@@ -587,6 +587,91 @@ __global__ void __launch_bounds__(256) power_rms_kernel(const PowArgs a)
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Hop buffers that do not fit shared memory (bin_e 16..21, src/rtl_power.c:485-491): the same arithmetic with the
+// work buffer in global memory, one launch per step of the reference's loop (:715-771).  A rare, bandwidth-heavy path
+// (the planner only gets here for sub-50-Hz bins); it exists for coverage, the shared-memory kernels are the product.
+//   big_load:  copy (:715-720) + boxcar (:723-733) + the two remove_dc sums (:609-624)
+//   big_window: (x - ave) * w with int16 wrap (:749-758), stored bit-reversed (fix_fft's swap pass, :275-290)
+//   big_stage:  one radix-2 stage over every N-block (:291-318)
+//   big_accum:  real_conj accumulate / peak hold (:760-768)
+__global__ void __launch_bounds__(256) power_big_load(const int16_t *src, uint32_t *work, int n_complex, int ds, long long *sums)
+{
+	const int n_out = (n_complex + ds - 1) / ds;
+	long long si = 0, sq = 0;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_out; k += gridDim.x * blockDim.x) {
+		int a = 0, b = 0;
+		const int e = (k + 1) * ds < n_complex ? (k + 1) * ds : n_complex;
+		for (int i = k * ds; i < e; i++) { a += src[2 * i]; b += src[2 * i + 1]; }
+		a = (int)(int16_t)a; b = (int)(int16_t)b;                 // the in-place int16 "+=" of the reference wraps
+		work[k] = ppack(a, b);
+		si += a; sq += b;
+	}
+	for (int o = 16; o > 0; o >>= 1) { si += __shfl_down_sync(0xffffffffu, si, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(reinterpret_cast<unsigned long long *>(sums), (unsigned long long)si);
+		atomicAdd(reinterpret_cast<unsigned long long *>(sums + 1), (unsigned long long)sq);
+	}
+}
+
+__global__ void __launch_bounds__(256) power_big_window(const uint32_t *work, uint32_t *fft, const int16_t *win, const long long *sums,
+                                                        int used_int16, int n_slots, int bin_e, int nblk)
+{
+	const int N = 1 << bin_e;
+	const int n_i = (used_int16 + 1) / 2, n_q = used_int16 / 2;
+	const int ave_i = (int)(int16_t)(sums[0] / (long long)used_int16);
+	const int ave_q = (int)(int16_t)(sums[1] / (long long)(used_int16 - 1));
+	const long long total = (long long)nblk * N;
+	for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+		const int i = (int)(g & (N - 1));
+		const long long base = g - i;
+		const int r = (int)(__brev((unsigned)i) >> (32 - bin_e));
+		// past the decimated span the reference transforms what the boxcar left there: a partial last slot, then zeros
+		const uint32_t u = g < n_slots ? work[g] : 0u;
+		const int w = win[i];
+		fft[base + r] = ppack((plo(u) - (g < n_i ? ave_i : 0)) * w, (phi(u) - (g < n_q ? ave_q : 0)) * w);
+	}
+}
+
+__global__ void __launch_bounds__(256) power_big_stage(uint32_t *fft, const int16_t *sine, int bin_e, int s, int nblk)
+{
+	const int N = 1 << bin_e;
+	const int l = 1 << s, k = bin_e - 1 - s;
+	const long long total = (long long)nblk * (N / 2);
+	for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+		const int t = (int)(g & (N / 2 - 1));
+		uint32_t *x = fft + (g - t) * 2;
+		const int m = t & (l - 1);
+		const int i = ((t >> s) << (s + 1)) + m, j = i + l;
+		const int jt = m << k;
+		const int wr = (int)sine[jt + N / 4] >> 1;
+		const int wi = (-(int)sine[jt]) >> 1;
+		const uint32_t u = x[i], v = x[j];
+		const int vr = plo(v), vi = phi(v);
+		const int tr = q15(wr, vr) - q15(wi, vi);
+		const int ti = q15(wr, vi) + q15(wi, vr);
+		const int qr = plo(u) >> 1, qi = phi(u) >> 1;
+		x[j] = ppack(qr - tr, qi - ti);
+		x[i] = ppack(qr + tr, qi + ti);
+	}
+}
+
+__global__ void __launch_bounds__(256) power_big_accum(const uint32_t *fft, long long *row, int bin_e, int nblk, int peak_hold)
+{
+	const int N = 1 << bin_e;
+	for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+		long long acc = row[j];
+		for (int b = 0; b < nblk; b++) {
+			const uint32_t w = fft[(size_t)b * N + j];
+			const int re = plo(w), im = phi(w);
+			const long long pw = (long long)(re * re) + (long long)(im * im);
+			if (peak_hold) { acc = pw > acc ? pw : acc; } else { acc += pw; }
+		}
+		row[j] = acc;
+	}
+}
+
 }  // namespace rxb
 
 using namespace rxb;
@@ -615,6 +700,7 @@ struct rxb200_power {
 	cudaEvent_t ev0, ev1;
 	void *d_db = nullptr; size_t db_cap = 0;   // csv_dbm staging (rxb200_power_read_db)
 	int triv = 0;                              // see PowArgs::triv
+	uint32_t *d_work = nullptr, *d_fft = nullptr; long long *d_sums = nullptr;   // global-memory path (hop buffer beyond shared memory)
 	int force_v1 = 0;                          // RXB200_POWER_V1 (A/B knob, read once at create): generic kernel only
 	int fft8_threads = 0;                      // RXB200_POWER_THREADS = 512 | 1024 (A/B knob): CTA width of the fast path
 };
@@ -630,8 +716,13 @@ static int power_validate(const rxb200_power_params *p)
 			return RXB200_EINVAL;
 		}
 		long long need = 16 + 256 + (long long)p->buf_len * 2;     // tables move to global memory when they do not fit
-		if (need > 227 * 1024 || (long long)(2 << p->bin_e) * p->downsample > p->buf_len) {
-			set_error("bin_e %d with buf_len %d does not fit shared memory", p->bin_e, p->buf_len);
+		if ((long long)(2 << p->bin_e) * p->downsample > p->buf_len) {
+			set_error("bin_e %d x downsample %d needs more than buf_len %d", p->bin_e, p->downsample, p->buf_len);
+			return RXB200_EINVAL;
+		}
+		if (need > 227 * 1024 && p->downsample > 1 && !p->boxcar) {
+			// the global-memory path (hop buffers beyond shared memory) carries the boxcar decimator only
+			set_error("bin_e %d with buf_len %d and -F decimation is not implemented (hop buffer beyond shared memory)", p->bin_e, p->buf_len);
 			return RXB200_EUNSUPPORTED;
 		}
 		// the block loop runs while offset < buf_len/downsample (src/rtl_power.c:747): a partial last block is
@@ -699,7 +790,7 @@ extern "C" void rxb200_power_destroy(rxb200_power *h)
 	if (!h) { return; }
 	cudaSetDevice(h->device);
 	if (h->stream) { cudaStreamSynchronize(h->stream); }
-	cudaFree(h->d_avg); cudaFree(h->d_samples); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_db);
+	cudaFree(h->d_avg); cudaFree(h->d_samples); cudaFree(h->d_sine); cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_db); cudaFree(h->d_work); cudaFree(h->d_fft); cudaFree(h->d_sums);
 	if (h->ev0) { cudaEventDestroy(h->ev0); }
 	if (h->ev1) { cudaEventDestroy(h->ev1); }
 	if (h->stream) { cudaStreamDestroy(h->stream); }
@@ -775,6 +866,34 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass; }                      // :428
 	} else {
 		const int N = 1 << h->p.bin_e;
+		if (16 + 256 + (size_t)h->p.buf_len * 2 > 227 * 1024) {
+			// ---- hop buffer beyond shared memory: the reference's loop step by step on a global work buffer
+			const int n_complex = h->p.buf_len / 2, ds = h->p.downsample;
+			const int used = h->p.buf_len / ds;                         // int16 span after decimation (:744-747)
+			const int nblk = (used + 2 * N - 1) / (2 * N);
+			if (!h->d_work) {
+				RXB_CUDA(cudaMalloc(&h->d_work, (size_t)n_complex * sizeof(uint32_t)));
+				RXB_CUDA(cudaMalloc(&h->d_fft, (size_t)nblk * N * sizeof(uint32_t)));
+				RXB_CUDA(cudaMalloc(&h->d_sums, 2 * sizeof(long long)));
+			}
+			const int g = h->n_sm * 8;
+			for (int pass = 0; pass < n_pass; pass++) {
+				for (int hl = 0; hl < nh; hl++) {
+					const int16_t *src = d_hop_bufs + ((size_t)pass * nh + hl) * (size_t)h->p.buf_len;
+					RXB_CUDA(cudaMemsetAsync(h->d_sums, 0, 2 * sizeof(long long), h->stream));
+					power_big_load<<<g, 256, 0, h->stream>>>(src, h->d_work, n_complex, ds, h->d_sums);
+					power_big_window<<<g, 256, 0, h->stream>>>(h->d_work, h->d_fft, h->d_window, h->d_sums, used, (n_complex + ds - 1) / ds, h->p.bin_e, nblk);
+					for (int st = 0; st < h->p.bin_e; st++) { power_big_stage<<<g, 256, 0, h->stream>>>(h->d_fft, h->d_sine, h->p.bin_e, st, nblk); }
+					power_big_accum<<<g, 256, 0, h->stream>>>(h->d_fft, h->d_avg + (size_t)(hop_begin + hl) * N, h->p.bin_e, nblk, h->p.peak_hold);
+					RXB_CUDA(cudaGetLastError());
+				}
+			}
+			for (int i = hop_begin; i < hop_end; i++) { h->samples[i] += n_pass * nblk * ds; }           // :769
+			RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
+			h->launches = n_pass * nh * (3 + h->p.bin_e);
+			if (sync) { RXB_CUDA(cudaStreamSynchronize(h->stream)); }
+			return RXB200_OK;
+		}
 		size_t smem = 16 + 256 + (size_t)h->p.buf_len * 2 + (size_t)((N * 3 / 4 + 7) & ~7) * 2 + (size_t)N * 2;
 		a.tables_in_smem = 1;
 		if (smem > 227 * 1024) { smem = 16 + 256 + (size_t)h->p.buf_len * 2; a.tables_in_smem = 0; }

@@ -158,3 +158,20 @@ def test_sdr_conversions_port_equals_golden(port):
     y, n12 = SI.cs12_capture(), SI.N_ELEMS_12
     mine = _port_sdr(port, "orx_sdr_cs12_to_cs16", y, np.empty(2 * n12, np.int16), n12)
     assert digest(mine.view(np.uint8)) == g["CS12_CS16"]["output_sha256"]
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("freq", ["100M:102.8M:40", "100M:100.4M:2"])
+def test_power_port_equals_reference_beyond_65536_bins(freq, port, ref_power):
+    """bin_e 17 / 18 (hop buffers of 0.5 / 7 MB, the second one boxcar-decimated by 7): the shapes the library serves from
+    global memory (tests/test_power_gpu.py::test_hop_buffers_beyond_shared_memory)."""
+    import oracle
+    rp = ref_power.setup(freq, 0.0, 1, 0, 0, "blackman")
+    assert rp.bin_e >= 17
+    rng = np.random.default_rng(rp.bin_e)
+    x = rng.integers(-3000, 3001, size=(2, rp.tune_count, rp.buf_len), dtype=np.int32).astype(np.int16)
+    avg, smp = ref_power.scan(x, 2)
+    win, _ = ref_power.tables()
+    pp = oracle.PowerParams(bin_e=rp.bin_e, buf_len=rp.buf_len, downsample=rp.downsample, downsample_passes=rp.downsample_passes)
+    a2, s2 = port.power_scan(pp, win, x, 2, rp.tune_count)
+    assert np.array_equal(smp, s2) and np.array_equal(avg, a2)

@@ -148,3 +148,23 @@ def test_csv_dbm_on_device(case, port):
     assert np.array_equal(np.isfinite(db[:, :-1]), fin)
     assert np.allclose(db[:, :-1][fin], want[fin], rtol=0, atol=1e-12)
     sc.close()
+
+
+@pytest.mark.parametrize("freq,n_pass", [("100M:102.8M:40", 2), ("100M:100.4M:2", 2), ("100M:105M:2", 1)])
+def test_hop_buffers_beyond_shared_memory(freq, n_pass, port):
+    """bin_e 16..21 (src/rtl_power.c:485-491): the hop buffer (2 N ds int16) no longer fits shared memory and the library
+    takes the global-memory path -- same integers as the oracle, boxcar decimation included."""
+    plan = power.plan_range(freq)
+    assert plan.bin_e >= 16 and plan.buf_len * 2 > 227 * 1024
+    rng = np.random.default_rng(plan.bin_e)
+    x = rng.integers(-3000, 3001, size=(n_pass, plan.n_hops, plan.buf_len), dtype=np.int32).astype(np.int16)
+    win = power.window_table("blackman", 1 << plan.bin_e)
+    sc = power.PowerScanner(plan, win)
+    sc.scanner(x, n_pass)
+    avg, smp = sc.read()
+    pp = oracle.PowerParams(bin_e=plan.bin_e, buf_len=plan.buf_len, downsample=plan.downsample,
+                            downsample_passes=plan.downsample_passes, comp_fir_size=plan.comp_fir_size, boxcar=plan.boxcar)
+    want, wsmp = port.power_scan(pp, win, x, n_pass, plan.n_hops)
+    assert np.array_equal(smp, wsmp)
+    assert np.array_equal(avg, want)
+    sc.close()
