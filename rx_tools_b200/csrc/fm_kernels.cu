@@ -47,6 +47,7 @@ struct FmDev {
 	int deemph, a, a_half, a_even;
 	unsigned a_magic; int a_K, a_use_magic;   // floor(n/a) == umulhi(n, a_magic) for the n range used
 	int resample, fast, slow, lpr_div;
+	int lpr_ok, lpr_m, lpr_s, lpr_add;        // acc / lpr_div (C truncation) == ((mulhi(acc, lpr_m) [+ acc]) >> lpr_s) + sign, host-verified
 	int offset_tuning;
 	int squelch, rdc_on, rdc_k, adc_on, adc_k;   // per-chunk reduction stages (src/rtl_fm.c:781-790, :699-721, :684-697)
 	int levels;                                  // keep per-chunk rms() (-L, src/rtl_fm.c:792-806)
@@ -726,6 +727,39 @@ __device__ __forceinline__ int adc_apply(const FmDev &c, AdcCtx &a, int m_rel, i
 // group then has floor(fast/slow) samples, or one more when that does not yet reach `fast` (only the
 // group a call inherits from the previous call can start with a larger phase).
 // m is the running (buffer-relative) PCM index; avg the running de-emphasis state.
+// The common shape of back_outputs -- de-emphasis on the reciprocal path, resampler on, every group regular (phase
+// below `slow` at the first group's start), no audio DC block -- without the run-time switches: 32-bit counters, the
+// group's quotient by a host-verified multiply-high, the next sample fetched one step ahead.  Same integers.
+template <bool EVEN, int PAD>
+__device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, int n_out,
+                                                  int &m, int &avg, int acc, int phase)
+{
+	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
+	const unsigned magic = c.a_magic;
+	const int lf = c.lpr_div, slow = c.slow, fast = c.fast;
+	const int dm = c.lpr_m, dsh = c.lpr_s, dadd = c.lpr_add;
+	int mm = m, a = avg;
+	int x = n_out > 0 ? pcm_load<PAD>(pcm_s, mm) : 0;
+	for (int n = 0; n < n_out; n++) {
+		int len = lf, ph = phase + lf * slow;
+		if (ph < fast) { len++; ph += slow; }
+		phase = ph - fast;
+		for (int j = 0; j < len; j++) {
+			const int xn = pcm_load<PAD>(pcm_s, mm + 1);   // one entry of slack exists past the last sample
+			a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
+			acc += wrap16(a);
+			x = xn; mm++;
+		}
+		int q = __mulhi(acc, dm);
+		if (dadd) { q += acc; }
+		q >>= dsh;
+		q += (int)((unsigned)q >> 31);
+		out[n] = (int16_t)q;
+		acc = 0;
+	}
+	m = mm; avg = a;
+}
+
 template <bool EVEN, int PAD>
 __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out,
                                              long long oa, long long ob, int &m, int &avg, int acc, int phase,
@@ -735,6 +769,10 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 	const unsigned magic = c.a_magic;
 	const int lf = c.resample ? c.fast / c.slow : 1;
 	const bool fast_path = c.deemph && c.a_use_magic;
+	if (fast_path && c.resample && c.lpr_ok && phase < c.slow && ax == nullptr && store) {
+		back_outputs_lean<EVEN, PAD>(c, pcm_s, out + oa, (int)(ob - oa), m, avg, acc, phase);
+		return;
+	}
 	int x = (oa < ob) ? pcm_load<PAD>(pcm_s, m) : 0;
 	for (long long o = oa; o < ob; o++) {
 		int len = 1;
@@ -1454,6 +1492,31 @@ static void fm_fill_dev(rxb200_fm *h)
 	}
 	d.resample = (p.rate_out2 > 0 && p.mode != RXB200_MODE_RAW) ? 1 : 0;
 	d.fast = p.rate_out; d.slow = p.rate_out2; d.lpr_div = d.resample ? (p.rate_out / p.rate_out2) : 1;
+	d.lpr_ok = 0;
+	if (d.resample && d.lpr_div >= 2 && d.lpr_div <= 4096) {
+		// signed division by a constant (Hacker's Delight 10-1), then checked for every sum a group can reach
+		const unsigned two31 = 0x80000000u, ad = (unsigned)d.lpr_div;
+		const unsigned anc = two31 - 1 - (two31 % ad);
+		int pw = 31;
+		unsigned q1 = two31 / anc, r1 = two31 - q1 * anc, q2 = two31 / ad, r2 = two31 - q2 * ad, delta;
+		do {
+			pw++;
+			q1 = 2 * q1; r1 = 2 * r1; if (r1 >= anc) { q1++; r1 -= anc; }
+			q2 = 2 * q2; r2 = 2 * r2; if (r2 >= ad) { q2++; r2 -= ad; }
+			delta = ad - r2;
+		} while (q1 < delta || (q1 == delta && r1 == 0));
+		d.lpr_m = (int)(q2 + 1); d.lpr_s = pw - 32; d.lpr_add = d.lpr_m < 0 ? 1 : 0;
+		bool ok = true;
+		const long long lim = (long long)(d.lpr_div + 2) * 32768;
+		for (long long n = -lim; n <= lim && ok; n++) {
+			long long q = ((long long)(int)n * (long long)d.lpr_m) >> 32;
+			if (d.lpr_add) { q += n; }
+			q >>= d.lpr_s;
+			q += (long long)((unsigned)(int)q >> 31);
+			if ((int)q != (int)n / d.lpr_div) { ok = false; }
+		}
+		d.lpr_ok = ok ? 1 : 0;
+	}
 	d.offset_tuning = p.offset_tuning;
 	for (int j = 0; j < 6; j++) { d.fir[j] = k_droop9_host[d.P][j]; }
 	d.fir_bias = (int)((unsigned)FIR_B * (2u * (unsigned)(d.fir[1] + d.fir[2] + d.fir[3] + d.fir[4]) + (unsigned)d.fir[5]));
