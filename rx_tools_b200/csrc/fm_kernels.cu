@@ -413,7 +413,7 @@ __device__ __forceinline__ long long out_before(const FmDev &c, long long m, int
 // entries) nor the back-end loads (lane stride = piece) pile on one bank.  The segment front end uses 2 (4 bytes);
 // the row front end 8, which keeps its 8/16-byte vector stores aligned (fm_rows.cuh)
 #define PCM_PAD_SEG 2
-#define PCM_PAD_ROWS 8
+#define PCM_PAD_ROWS 0
 template <int PAD>
 __device__ __forceinline__ int pcm_phys(int rel) { return rel + PAD * (rel >> 7); }
 
@@ -1557,7 +1557,11 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = ROWS_BE_LANES;
 		h->env_seg = getenv("RXB200_FM_SEG") ? atoll(getenv("RXB200_FM_SEG")) : 0;
 		h->env_be_lanes = getenv("RXB200_FM_BE_LANES") ? atoi(getenv("RXB200_FM_BE_LANES")) : 0;
-		h->segs_min = getenv("RXB200_FM_SEGS_MIN") ? (size_t)atoll(getenv("RXB200_FM_SEGS_MIN")) : (size_t)148 * 32768;
+		// measured on fm2a (profiles/r2_*): with de-emphasis at the capture rate the back end is a latency-bound chain of
+		// 16 a + 64 replay steps per piece and the split kernel's four back-end warps per SM finish an item later
+		// than the fused kernel's six (68 vs 85 Gsamples/s) -- the path stays behind a switch until the back end
+		// carries several pieces per lane
+		h->segs_min = getenv("RXB200_FM_SEGS_MIN") ? (size_t)atoll(getenv("RXB200_FM_SEGS_MIN")) : (size_t)-1;
 		{
 			// A/B knobs, read once at create: back-end lanes (32 | 64 ...) of the split kernel
 			const char *e = getenv("RXB200_FM_ROWS_BE");
