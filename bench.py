@@ -88,7 +88,7 @@ def peaks():
 def kernel_source_sha(workload):
     """Hash of the CUDA sources behind a workload's dominant kernel: profiles/traffic_*.json carries it, so a dram-bytes
     figure measured on an older kernel is reported as stale instead of being passed on."""
-    names = ["fm_kernels.cu", "common.cuh"] if workload.startswith("fm") else ["power_kernels.cu", "common.cuh"]
+    names = ["fm_kernels.cu", "fm_rows.cuh", "common.cuh"] if workload.startswith("fm") else ["power_kernels.cu", "common.cuh"]
     h = hashlib.sha256()
     for n in names:
         with open(os.path.join(ROOT, "rx_tools_b200", "csrc", n), "rb") as f:

@@ -730,31 +730,52 @@ __device__ __forceinline__ int adc_apply(const FmDev &c, AdcCtx &a, int m_rel, i
 // The common shape of back_outputs -- de-emphasis on the reciprocal path, resampler on, every group regular (phase
 // below `slow` at the first group's start), no audio DC block -- without the run-time switches: 32-bit counters, the
 // group's quotient by a host-verified multiply-high, the next sample fetched one step ahead.  Same integers.
-template <bool EVEN, int PAD>
+// LF: the integer rate ratio fast/slow when it is a compile-time value (a group is LF or LF + 1 samples: LF unrolled
+// steps and one conditional one), 0: any ratio (loop).
+template <bool EVEN, int PAD, int LF>
 __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, int n_out,
                                                   int &m, int &avg, int acc, int phase)
 {
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
-	const int lf = c.lpr_div, slow = c.slow, fast = c.fast;
+	const int lf = LF > 0 ? LF : c.lpr_div, slow = c.slow, fast = c.fast;
 	const int dm = c.lpr_m, dsh = c.lpr_s, dadd = c.lpr_add;
-	int mm = m, a = avg;
-	int x = n_out > 0 ? pcm_load<PAD>(pcm_s, mm) : 0;
+	const int16_t *p = pcm_s + pcm_phys<PAD>(m);        // PAD == 0 here: consecutive samples are consecutive entries
+	int a = avg, mm = m;
+	int16_t *op = out;
 	for (int n = 0; n < n_out; n++) {
-		int len = lf, ph = phase + lf * slow;
-		if (ph < fast) { len++; ph += slow; }
+		int ph = phase + lf * slow;
+		const bool extra = ph < fast;
+		if (extra) { ph += slow; }
 		phase = ph - fast;
-		for (int j = 0; j < len; j++) {
-			const int xn = pcm_load<PAD>(pcm_s, mm + 1);   // one entry of slack exists past the last sample
-			a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
-			acc += wrap16(a);
-			x = xn; mm++;
+		if constexpr (LF > 0 && PAD == 0) {
+#pragma unroll
+			for (int j = 0; j < LF; j++) {
+				const int x = p[j];
+				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
+				acc += wrap16(a);
+			}
+			if (extra) {
+				const int x = p[LF];
+				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
+				acc += wrap16(a);
+			}
+			p += LF + (extra ? 1 : 0);
+			mm += LF + (extra ? 1 : 0);
+		} else {
+			const int len = lf + (extra ? 1 : 0);
+			for (int j = 0; j < len; j++) {
+				const int x = pcm_load<PAD>(pcm_s, mm);
+				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
+				acc += wrap16(a);
+				mm++;
+			}
 		}
 		int q = __mulhi(acc, dm);
 		if (dadd) { q += acc; }
 		q >>= dsh;
 		q += (int)((unsigned)q >> 31);
-		out[n] = (int16_t)q;
+		*op++ = (int16_t)q;
 		acc = 0;
 	}
 	m = mm; avg = a;
@@ -770,7 +791,10 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 	const int lf = c.resample ? c.fast / c.slow : 1;
 	const bool fast_path = c.deemph && c.a_use_magic;
 	if (fast_path && c.resample && c.lpr_ok && phase < c.slow && ax == nullptr && store) {
-		back_outputs_lean<EVEN, PAD>(c, pcm_s, out + oa, (int)(ob - oa), m, avg, acc, phase);
+		// the two ratios the wbfm presets produce get unrolled bodies (300 k -> 48 k: 6, 170 k -> 32 k: 5)
+		if (PAD == 0 && c.lpr_div == 6) { back_outputs_lean<EVEN, PAD, 6>(c, pcm_s, out + oa, (int)(ob - oa), m, avg, acc, phase); }
+		else if (PAD == 0 && c.lpr_div == 5) { back_outputs_lean<EVEN, PAD, 5>(c, pcm_s, out + oa, (int)(ob - oa), m, avg, acc, phase); }
+		else { back_outputs_lean<EVEN, PAD, 0>(c, pcm_s, out + oa, (int)(ob - oa), m, avg, acc, phase); }
 		return;
 	}
 	int x = (oa < ob) ? pcm_load<PAD>(pcm_s, m) : 0;
@@ -1343,14 +1367,17 @@ static fm_kernel_fn pick_kernel_p(int P, int threads)
 // the split kernel with the row front end exists for the wbfm shape with 1..3 packed passes
 // CTA shape of the split kernel (overridable for A/B builds, tools/build_variants.sh): front-end warps, back-end lanes,
 // CTAs per SM the register budget is cut for
+// Measured on fm2b (profiles/r2_ab_shapes.txt): four CTAs of 4 + 1 warps beat two of 8 + 2 (smaller items: a shorter
+// tail when the grid drains), one back-end warp per four front-end warps is the ratio at which the front end stops
+// waiting for PCM buffers; 3 CTAs x (6 + 1) and 1 CTA x (16 + 4) lose.
 #ifndef ROWS_FE_WARPS
-#define ROWS_FE_WARPS 8
+#define ROWS_FE_WARPS 4
 #endif
 #ifndef ROWS_BE_LANES
-#define ROWS_BE_LANES 64
+#define ROWS_BE_LANES 32
 #endif
 #ifndef ROWS_MINB
-#define ROWS_MINB 2
+#define ROWS_MINB 4
 #endif
 #define ROWS_TMAX (ROWS_FE_WARPS * 32 + ROWS_BE_LANES)
 static fm_kernel_fn pick_rows_kernel(int P, int fir_on)
