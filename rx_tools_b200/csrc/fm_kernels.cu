@@ -1367,17 +1367,17 @@ static fm_kernel_fn pick_kernel_p(int P, int threads)
 // the split kernel with the row front end exists for the wbfm shape with 1..3 packed passes
 // CTA shape of the split kernel (overridable for A/B builds, tools/build_variants.sh): front-end warps, back-end lanes,
 // CTAs per SM the register budget is cut for
-// Measured on fm2b (profiles/r2_ab_shapes.txt): four CTAs of 4 + 1 warps beat two of 8 + 2 (smaller items: a shorter
-// tail when the grid drains), one back-end warp per four front-end warps is the ratio at which the front end stops
-// waiting for PCM buffers; 3 CTAs x (6 + 1) and 1 CTA x (16 + 4) lose.
+// Measured on fm2b (profiles/r2_ab_shapes.txt): two CTAs of 8 + 2 warps (longer items: less replay per sample) ahead
+// of four of 4 + 1; one back-end warp per four front-end warps is the ratio at which the front end stops waiting for
+// PCM buffers; 3 CTAs x (6 + 1) and 1 CTA x (16 + 4) lose.
 #ifndef ROWS_FE_WARPS
-#define ROWS_FE_WARPS 4
+#define ROWS_FE_WARPS 8
 #endif
 #ifndef ROWS_BE_LANES
-#define ROWS_BE_LANES 32
+#define ROWS_BE_LANES 64
 #endif
 #ifndef ROWS_MINB
-#define ROWS_MINB 4
+#define ROWS_MINB 2
 #endif
 #define ROWS_TMAX (ROWS_FE_WARPS * 32 + ROWS_BE_LANES)
 static fm_kernel_fn pick_rows_kernel(int P, int fir_on)
