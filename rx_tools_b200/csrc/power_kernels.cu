@@ -902,9 +902,17 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 		if (fast) {
 			// one CTA per (hop, pass-slice); 1024 threads: ~1 CTA per SM resident, 512 threads: 2
 			const int threads = fft8_threads(h->p.bin_e, h->fft8_threads);
-			int sl = (h->n_sm * (1024 / threads) + nh - 1) / nh;
-			if (sl > n_pass) { sl = n_pass; }
-			if (sl < 1) { sl = 1; }
+			// slices of the passes per hop: the launch takes ceil(nh*sl / resident CTAs) rounds of ceil(n_pass / sl) hop
+			// buffers each -- pick the split with the fewest buffer-times (a sharded rank owns few hops: 109 of 871 at
+			// eight GPUs, where "about one CTA per slot" left 31 CTAs for a second round of 12 buffers each)
+			const long long slots = (long long)h->n_sm * (1024 / threads);
+			int sl = 1;
+			long long best = -1;
+			for (int c = 1; c <= n_pass && c <= 64; c++) {
+				const long long rounds = ((long long)nh * c + slots - 1) / slots;
+				const long long t = rounds * ((n_pass + c - 1) / c) * 1000 + c;      // ties: fewer slices (fewer atomic flushes)
+				if (best < 0 || t < best) { best = t; sl = c; }
+			}
 			a.slices = sl;
 			const size_t sm8 = 16 + 512 + 2 * (8192 + 1024) * 4 + (size_t)(N / 2 > 4 ? N / 2 : 4) * 4 + (size_t)N * 2;
 			e = launch_fft8(h->p.bin_e, threads, a, nh * sl, sm8, h->stream);
