@@ -908,9 +908,10 @@ extern "C" int rxb200_power_accumulate_device(rxb200_power *h, const int16_t *d_
 			const long long slots = (long long)h->n_sm * (1024 / threads);
 			int sl = 1;
 			long long best = -1;
-			for (int c = 1; c <= n_pass && c <= 64; c++) {
+			for (int c = 1; c <= n_pass && (long long)c <= 2 * slots; c++) {
+				// + 1: a CTA's fixed cost (tables, accumulator flush) is about one hop buffer's worth of work
 				const long long rounds = ((long long)nh * c + slots - 1) / slots;
-				const long long t = rounds * ((n_pass + c - 1) / c) * 1000 + c;      // ties: fewer slices (fewer atomic flushes)
+				const long long t = rounds * ((n_pass + c - 1) / c + 1) * 4096 + c;   // ties: fewer slices (fewer atomic flushes)
 				if (best < 0 || t < best) { best = t; sl = c; }
 			}
 			a.slices = sl;

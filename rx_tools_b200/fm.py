@@ -84,7 +84,7 @@ class FmDemod:
         _lib.check(_lib.lib().rxb200_fm_create(C.byref(pc), device, n_channels, C.byref(self._h)))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h:
+        if _lib is not None and getattr(self, "_h", None) is not None and self._h:
             _lib.lib().rxb200_fm_destroy(self._h)
             self._h = None
 

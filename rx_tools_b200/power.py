@@ -89,7 +89,7 @@ class PowerScanner:
                                                   device, C.byref(self._h)))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h:
+        if _lib is not None and getattr(self, "_h", None) is not None and self._h:
             _lib.lib().rxb200_power_destroy(self._h)
             self._h = None
 
@@ -203,7 +203,7 @@ class Comm:
         return buf.raw
 
     def close(self) -> None:
-        if getattr(self, "_c", None) is not None and self._c:
+        if _lib is not None and getattr(self, "_c", None) is not None and self._c:
             _lib.lib().rxb200_comm_destroy(self._c)
             self._c = None
 
@@ -225,7 +225,7 @@ class PowerGroup:
         self.n_dev = n_dev
 
     def close(self) -> None:
-        if getattr(self, "_g", None) is not None and self._g:
+        if _lib is not None and getattr(self, "_g", None) is not None and self._g:
             _lib.lib().rxb200_power_group_destroy(self._g)
             self._g = None
 
