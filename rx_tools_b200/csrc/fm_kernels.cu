@@ -422,10 +422,12 @@ __device__ __forceinline__ int pcm_phys(int rel) { return rel + PAD * (rel >> 7)
 // rotation on, serial stages present — resolved at compile time.
 template <int SPEC>
 struct Spec {
-	static __device__ __forceinline__ int mode(const FmDev &c) { return SPEC == 1 ? RXB200_MODE_FM : c.mode; }
-	static __device__ __forceinline__ int atan_mode(const FmDev &c) { return SPEC == 1 ? RXB200_ATAN_FAST : c.atan_mode; }
-	static __device__ __forceinline__ bool rotate(const FmDev &c) { return SPEC == 1 ? true : !c.offset_tuning; }
-	static __device__ __forceinline__ bool direct(const FmCall &k) { return SPEC == 1 ? false : (k.direct_out != 0); }
+	// SPEC 3: the multi-channel NBFM shape (BASELINE configs[4]) -- FM discriminator through the LUT, rotation on, NO serial
+	// stage (the front end stores the output itself): the back end and every other mode drop out of the kernel at compile time
+	static __device__ __forceinline__ int mode(const FmDev &c) { return (SPEC == 1 || SPEC == 3) ? RXB200_MODE_FM : c.mode; }
+	static __device__ __forceinline__ int atan_mode(const FmDev &c) { return SPEC == 1 ? RXB200_ATAN_FAST : (SPEC == 3 ? RXB200_ATAN_LUT : c.atan_mode); }
+	static __device__ __forceinline__ bool rotate(const FmDev &c) { return (SPEC == 1 || SPEC == 3) ? true : !c.offset_tuning; }
+	static __device__ __forceinline__ bool direct(const FmCall &k) { return SPEC == 1 ? false : (SPEC == 3 ? true : (k.direct_out != 0)); }
 };
 
 struct EmitCtx {
@@ -1417,6 +1419,9 @@ static int rows_xs_words(int P) { return P == 1 ? RowSmem<1>::WORDS : (P == 2 ? 
 
 static fm_kernel_fn pick_kernel(int P, int spec, int threads)
 {
+#ifndef RXB_QUICK
+	if (spec == 3) { return P == 0 ? (threads == 128 ? fm_fused_kernel<0, 3, 128> : fm_fused_kernel<0, 3, 256>) : nullptr; }
+#endif
 	if (spec == 1 && P <= 4) { return pick_kernel_p<1>(P, threads); }
 	if (spec == 2) { return pick_kernel_p<2>(P, threads); }
 	return pick_kernel_p<0>(P, threads);
@@ -1576,8 +1581,10 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		// wbfm shape: FM + fast_atan2 + rotation, with a serial stage (de-emphasis or resampler)
 		const bool serial = (params->deemph != 0) || (params->rate_out2 > 0);
 		const bool plain = !params->squelch_level && !params->dc_block_audio && !params->dc_block_raw && params->post_downsample <= 1;
-		const int spec = h->wide ? 2 : ((params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
-		                                 !params->offset_tuning && serial && plain) ? 1 : 0);
+		int spec = h->wide ? 2 : ((params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_FAST &&
+		                           !params->offset_tuning && serial && plain) ? 1 : 0);
+		if (!h->wide && params->mode == RXB200_MODE_FM && params->custom_atan == RXB200_ATAN_LUT && !params->offset_tuning &&
+		    !serial && plain && params->downsample_passes == 0 && !getenv("RXB200_FM_NOSPEC3")) { spec = 3; }
 		h->threads = fm_cta_threads(params->downsample_passes, params->downsample);
 		h->kern = pick_kernel(params->downsample_passes, spec, h->threads);
 		h->spec = spec;
