@@ -87,6 +87,8 @@ struct FmCall {
 	int n_chunks;
 	int reduce_mode;          // 0 main pass, 1 squelch sums (t, p), 2 audio-DC sums
 	int one;                  // always 1 (see front_run)
+	const int16_t *pcm_g;     // fm_back_kernel: [n_ch][pcm_g_stride] PCM of the whole call in global memory (null elsewhere)
+	long long pcm_g_stride;
 };
 
 enum { ST_BOX_I = 0, ST_BOX_Q, ST_BOX_N, ST_PRE_I, ST_PRE_Q, ST_AVG, ST_LPR_ACC, ST_LPR_PHASE,
@@ -424,10 +426,12 @@ template <int SPEC>
 struct Spec {
 	// SPEC 3: the multi-channel NBFM shape (BASELINE configs[4]) -- FM discriminator through the LUT, rotation on, NO serial
 	// stage (the front end stores the output itself): the back end and every other mode drop out of the kernel at compile time
-	static __device__ __forceinline__ int mode(const FmDev &c) { return (SPEC == 1 || SPEC == 3) ? RXB200_MODE_FM : c.mode; }
-	static __device__ __forceinline__ int atan_mode(const FmDev &c) { return SPEC == 1 ? RXB200_ATAN_FAST : (SPEC == 3 ? RXB200_ATAN_LUT : c.atan_mode); }
-	static __device__ __forceinline__ bool rotate(const FmDev &c) { return (SPEC == 1 || SPEC == 3) ? true : !c.offset_tuning; }
-	static __device__ __forceinline__ bool direct(const FmCall &k) { return SPEC == 1 ? false : (SPEC == 3 ? true : (k.direct_out != 0)); }
+	// SPEC 4: the wbfm shape's front end alone -- SPEC 1's discriminator, the PCM stored to global memory through the
+	// direct-output path (fm_back_kernel runs the serial stages afterwards, fm_launch's stream path)
+	static __device__ __forceinline__ int mode(const FmDev &c) { return (SPEC == 1 || SPEC == 3 || SPEC == 4) ? RXB200_MODE_FM : c.mode; }
+	static __device__ __forceinline__ int atan_mode(const FmDev &c) { return (SPEC == 1 || SPEC == 4) ? RXB200_ATAN_FAST : (SPEC == 3 ? RXB200_ATAN_LUT : c.atan_mode); }
+	static __device__ __forceinline__ bool rotate(const FmDev &c) { return (SPEC == 1 || SPEC == 3 || SPEC == 4) ? true : !c.offset_tuning; }
+	static __device__ __forceinline__ bool direct(const FmCall &k) { return SPEC == 1 ? false : ((SPEC == 3 || SPEC == 4) ? true : (k.direct_out != 0)); }
 };
 
 struct EmitCtx {
@@ -584,6 +588,33 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 {
 	constexpr int PL = FrontState<P, SPEC>::PL;
 	const bool rot = Spec<SPEC>::rotate(c);
+	if constexpr (P == 0 && SPEC == 4) {
+		if (c.D == 1) {
+			// no decimation (-s at or above 1 Msps): every input sample is a PCM sample and a block is 8 consecutive entries of
+			// the global PCM array, 16-byte aligned (segments and halos are multiples of 8) -- one vector store per block
+			// instead of eight 2-byte stores to 32 different lines per warp.  Same arithmetic as post_decim's FM branch.
+			int a[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int di, dq;
+				scale_rot(v[j], j, rot, di, dq);
+				const int br = s.pre_i, bj = s.pre_q;
+				const int cr = add_w(mul_w(di, br), mul_w(dq, bj));
+				const int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
+				// F8: the chunk's first sample (chunks start on block boundaries) goes through the libm discriminator
+				a[j] = (j == 0 && e.first_in_chunk) ? disc_std(cr, cj) : fast_atan2_i(cj, cr);
+				s.pre_i = di; s.pre_q = dq;
+			}
+			e.first_in_chunk = 0;
+			if (STORE) {
+				uint4 w;
+				w.x = pack2(a[0], a[1]); w.y = pack2(a[2], a[3]); w.z = pack2(a[4], a[5]); w.w = pack2(a[6], a[7]);
+				*reinterpret_cast<uint4 *>(e.out + e.m_lo + e.rel) = w;
+			}
+			e.rel += 8;
+			return;
+		}
+	}
 	if constexpr (P == 0) {
 		// low_pass boxcar (src/rtl_fm.c:351-371)
 #pragma unroll
@@ -736,10 +767,11 @@ __device__ __forceinline__ int adc_apply(const FmDev &c, AdcCtx &a, int m_rel, i
 // steps and one conditional one), 0: any ratio (loop).
 template <bool EVEN, int PAD, int LF>
 __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, int n_out,
-                                                  int &m, int &avg, int acc, int phase)
+                                                  int &m, int &avg, int acc, int &phase_io)
 {
 	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
 	const unsigned magic = c.a_magic;
+	int phase = phase_io;
 	const int lf = LF > 0 ? LF : c.lpr_div, slow = c.slow, fast = c.fast;
 	const int dm = c.lpr_m, dsh = c.lpr_s, dadd = c.lpr_add;
 	const int16_t *p = pcm_s + pcm_phys<PAD>(m);        // PAD == 0 here: consecutive samples are consecutive entries
@@ -780,7 +812,7 @@ __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t 
 		*op++ = (int16_t)q;
 		acc = 0;
 	}
-	m = mm; avg = a;
+	m = mm; avg = a; phase_io = phase;
 }
 
 template <bool EVEN, int PAD>
@@ -817,6 +849,73 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 		}
 		if (store) { out[o] = (int16_t)(c.resample ? div_small_quotient(acc, c.lpr_div) : acc); }
 		acc = 0;
+	}
+}
+
+// ---- per-lane windows of global PCM staged through shared memory (fm_back_kernel).
+// A lane of the back kernel walks its own piece of the call's PCM: read straight from global memory that is one 2-byte
+// load per step to 32 different lines per warp -- 32 trips through the L1 tag stage per step, which at one PCM sample per
+// input sample (fm2a) costs more than the arithmetic.  Instead the warp copies, for each of its lanes in turn, the next
+// WIN_SAMPLES of that lane's piece with coalesced 4-byte loads into a row of shared memory (one line per load), and the
+// lanes then run the unchanged replay / output loops out of their rows.  Odd row stride: lanes reading the same offset
+// of their rows hit 32 different banks.
+#define WIN_SAMPLES 256
+#define WIN_ROW_WORDS (WIN_SAMPLES / 2 + 1)
+struct LaneWin {
+	const int16_t *g;         // the channel's PCM in global memory
+	uint32_t *rows;           // this warp's 32 rows
+	int lane;
+};
+// all 32 lanes: lane l's row <- g[base_l .. base_l + WIN_SAMPLES), base_l even
+__device__ __forceinline__ void win_fill(const LaneWin &w, int base)
+{
+	constexpr int NV = WIN_SAMPLES / 64;
+#pragma unroll 4
+	for (int l = 0; l < 32; l++) {
+		const int b = __shfl_sync(0xffffffffu, base, l);
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(w.g + b) + w.lane;
+		uint32_t *dst = w.rows + l * WIN_ROW_WORDS + w.lane;
+		uint32_t t[NV];
+#pragma unroll
+		for (int i = 0; i < NV; i++) { t[i] = __ldg(src + 32 * i); }
+#pragma unroll
+		for (int i = 0; i < NV; i++) { dst[32 * i] = t[i]; }
+	}
+}
+// back_replay over PCM [m, m_end) through windows; every lane of the warp takes part (an empty range for lanes with nothing to do)
+template <bool EVEN>
+__device__ __forceinline__ void win_replay(const FmDev &c, const LaneWin &w, int m, int m_end, int &lo, int &hi)
+{
+	const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + w.lane * WIN_ROW_WORDS);
+	while (__any_sync(0xffffffffu, m < m_end)) {
+		const int base = m & ~1;
+		win_fill(w, base);
+		__syncwarp();
+		const int e = m_end < base + WIN_SAMPLES ? m_end : base + WIN_SAMPLES;
+		if (m < e) { back_replay<EVEN, 0>(c, row - base, m, e, lo, hi); m = e; }
+		__syncwarp();
+	}
+}
+// back_outputs_lean for `remaining` outputs through windows: per window as many whole resampler groups as it holds
+template <bool EVEN>
+__device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin &w, int16_t *__restrict__ op, int remaining, int &m, int &avg,
+                                            int acc, int phase)
+{
+	const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + w.lane * WIN_ROW_WORDS);
+	const int lf1 = c.lpr_div + 1;
+	while (__any_sync(0xffffffffu, remaining > 0)) {
+		const int base = m & ~1;
+		win_fill(w, base);
+		__syncwarp();
+		int n = (base + WIN_SAMPLES - m) / lf1;
+		if (n > remaining) { n = remaining; }
+		if (n > 0) {
+			if (c.lpr_div == 6) { back_outputs_lean<EVEN, 0, 6>(c, row - base, op, n, m, avg, acc, phase); }
+			else if (c.lpr_div == 5) { back_outputs_lean<EVEN, 0, 5>(c, row - base, op, n, m, avg, acc, phase); }
+			else { back_outputs_lean<EVEN, 0, 0>(c, row - base, op, n, m, avg, acc, phase); }
+			op += n; remaining -= n; acc = 0;
+		}
+		__syncwarp();
 	}
 }
 
@@ -925,7 +1024,7 @@ __device__ __forceinline__ Item make_item(const FmDev &c, const FmCall &k, int w
 	long long own_hi = own_lo + (long long)k.n_own * k.Sf;
 	if (own_hi > k.n) { own_hi = k.n; }
 	long long buf_lo = own_lo - (long long)k.n_extra * k.Sf;
-	if (buf_lo < 0) { buf_lo = 0; }
+	if (buf_lo < 0 || k.pcm_g) { buf_lo = 0; }      // global PCM: the buffer is the whole call, indices are absolute
 	it.m_lo = dec_before(c, buf_lo, it.box_n0);
 	it.m_own = (int)(dec_before(c, own_lo, it.box_n0) - it.m_lo);
 	it.m_hi = (int)(dec_before(c, own_hi, it.box_n0) - it.m_lo);
@@ -1007,14 +1106,33 @@ __device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, 
 	if (ax) { adc_flush(*ax); }
 }
 
+// run_piece through windows (fm_back_kernel): every lane of the warp calls it, `run` says whether this lane has a piece to run
+__device__ __forceinline__ void run_piece_win(const FmDev &c, const LaneWin &w, int16_t *__restrict__ out, const Piece &p,
+                                              int &m_run, int &avg, AdcCtx *ax, bool store, bool run)
+{
+	const bool lean = run && c.deemph && c.a_use_magic && c.resample && c.lpr_ok && p.ph0 < c.slow && ax == nullptr && store &&
+	                  2 * (c.lpr_div + 1) <= WIN_SAMPLES;
+	int m = p.ga, a = avg;
+	const int n_out = lean ? (int)(p.ob - p.oa) : 0;
+	if (c.a_even) { win_outputs<true>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
+	else { win_outputs<false>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
+	if (lean) { m_run = m; avg = a; }
+	else if (run) { run_piece<0>(c, w.g, out, p, m_run, avg, ax, store); }      // any other shape: straight from global memory
+}
+
 #define FM_BE_MAX_LANES 256
 #define BAR_BE 1                 // named barrier of the back-end warps (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int SPEC, int PAD>
+// WIN: the PCM is the call's global array and replay / outputs go through per-lane windows in `win_rows` (fm_back_kernel;
+// whole warps call, every lane takes part in the window fills)
+template <int SPEC, int PAD, bool WIN = false>
 __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
-                                          const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok, int *s_start)
+                                          const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok, int *s_start,
+                                          uint32_t *win_rows = nullptr)
 {
+	LaneWin lw;
+	lw.g = pcm_s; lw.rows = win_rows; lw.lane = q & 31;
 	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
 	int16_t *__restrict__ out = k.out + (size_t)it.ch * (size_t)k.out_stride;
 	const bool last_cta = (it.b == k.n_cta - 1);
@@ -1037,14 +1155,23 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	int kind = PK_EXACT;
 	{
 		int lo = -32768, hi = 32767, avg = 0, m_run = p.ga;
-		if (active || q == 0) {
-			int ws = p.ga - k.W_dec;
-			if (ws < 0) { ws = 0; }
-			ws &= ~3;           // quad-aligned start: a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
-			if (it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
-			if (c.deemph) {
-				if (c.a_even) { back_replay<true, PAD>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false, PAD>(c, pcm_s, ws, p.ga, lo, hi); }
+		const bool need = active || q == 0;
+		int ws = p.ga - k.W_dec;
+		if (ws < 0) { ws = 0; }
+		ws &= ~3;           // quad-aligned start: a longer replay only tightens the bracket; every buffer entry from 0 on is exact PCM
+		if (need && it.m_lo == 0 && ws == 0) { lo = hi = (int)carry[ST_AVG]; }
+		bool replayed = false;
+		if constexpr (WIN) {
+			if (c.deemph && c.a_use_magic) {
+				const int r_end = need ? p.ga : ws;
+				if (c.a_even) { win_replay<true>(c, lw, ws, r_end, lo, hi); } else { win_replay<false>(c, lw, ws, r_end, lo, hi); }
+				replayed = true;
 			}
+		}
+		if (!replayed && need && c.deemph) {
+			if (c.a_even) { back_replay<true, PAD>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false, PAD>(c, pcm_s, ws, p.ga, lo, hi); }
+		}
+		if (need) {
 			avg = lo;
 			if (c.deemph && lo != hi) {
 				// Open bracket (quiet input: the rounding IIR has a dead zone).  Summarise what the piece does to
@@ -1057,7 +1184,8 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 				avg = lo; m_run = ge;
 			}
 		}
-		if (active && kind == PK_EXACT) { run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store); }
+		if constexpr (WIN) { run_piece_win(c, lw, out, p, m_run, avg, ax, store, active && kind == PK_EXACT); }
+		else { if (active && kind == PK_EXACT) { run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store); } }
 		s_avg[q] = avg; s_mrun[q] = m_run; s_ok[q] = (unsigned char)kind;
 	}
 	bar_sync(BAR_BE, lanes);
@@ -1120,9 +1248,15 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 	}
 	bar_sync(BAR_BE, lanes);
 	// ---- pass 2: the pieces that had no exact start in pass 1 now run from the state the chain gave them
-	if (active && kind != PK_EXACT) {
-		int avg = s_start[q], m_run = p.ga;
-		run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store);
+	if constexpr (WIN) {
+		const bool run = active && kind != PK_EXACT;
+		int avg = run ? s_start[q] : 0, m_run = p.ga;
+		run_piece_win(c, lw, out, p, m_run, avg, ax, store, run);
+	} else {
+		if (active && kind != PK_EXACT) {
+			int avg = s_start[q], m_run = p.ga;
+			run_piece<PAD>(c, pcm_s, out, p, m_run, avg, ax, store);
+		}
 	}
 	if (q != 0) { return; }
 	// end state of the item = state after its last piece
@@ -1180,6 +1314,32 @@ __global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3
 		}
 		__syncthreads();
 		if (tid < k.be_lanes) { back_item<SPEC, PCM_PAD_SEG>(c, k, it, work, tid, k.be_lanes, pcm_s, s_avg, s_mrun, s_ok, s_start); }
+	}
+}
+
+// ---- back end alone, over PCM in global memory (stream path: the front end of the whole call ran first).
+// An item is a stretch of the call's PCM, a piece (one lane) a run of outputs in it.  With the PCM of the whole call
+// at hand a piece can be as long as the launch has lanes to spare for, so the 16 a + 64 replay steps in front of every
+// piece are paid once per few thousand samples, not once per shared-memory buffer share.  Same pieces, brackets,
+// look-back and integers as back_item everywhere else.
+#define BACK_T 128
+__global__ void __launch_bounds__(BACK_T) fm_back_kernel(const FmDev c, const FmCall k)
+{
+	extern __shared__ __align__(16) uint32_t win_s[];      // [BACK_T / 32][32][WIN_ROW_WORDS]
+	__shared__ int s_work;
+	__shared__ int s_avg[BACK_T], s_mrun[BACK_T], s_start[BACK_T];
+	__shared__ unsigned char s_ok[BACK_T];
+	const int tid = threadIdx.x;
+	const int total_work = k.n_ch * k.n_cta;
+	uint32_t *rows = win_s + (size_t)(tid >> 5) * 32 * WIN_ROW_WORDS;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) { s_work = atomicAdd(k.ticket, 1); }
+		__syncthreads();
+		const int work = s_work;
+		if (work >= total_work) { break; }
+		const Item it = make_item(c, k, work);
+		back_item<1, 0, true>(c, k, it, work, tid, BACK_T, k.pcm_g + (size_t)it.ch * (size_t)k.pcm_g_stride, s_avg, s_mrun, s_ok, s_start, rows);
 	}
 }
 
@@ -1422,6 +1582,7 @@ static fm_kernel_fn pick_kernel(int P, int spec, int threads)
 #ifndef RXB_QUICK
 	if (spec == 3) { return P == 0 ? (threads == 128 ? fm_fused_kernel<0, 3, 128> : fm_fused_kernel<0, 3, 256>) : nullptr; }
 #endif
+	if (spec == 4) { return P == 0 ? (threads == 128 ? fm_fused_kernel<0, 4, 128> : fm_fused_kernel<0, 4, 256>) : nullptr; }
 	if (spec == 1 && P <= 4) { return pick_kernel_p<1>(P, threads); }
 	if (spec == 2) { return pick_kernel_p<2>(P, threads); }
 	return pick_kernel_p<0>(P, threads);
@@ -1469,6 +1630,9 @@ struct rxb200_fm {
 	fm_kernel_fn kern;
 	fm_kernel_fn kern_rows;        // split kernel with the row front end (null: shape not covered)
 	fm_kernel_fn kern_segs;        // split kernel with the segment front end (null: shape not covered)
+	fm_kernel_fn kern_front;       // stream path: front end alone (SPEC 4), PCM to global memory; fm_back_kernel follows
+	int16_t *d_pcm; size_t d_pcm_cap;   // its PCM scratch, int16 elements
+	size_t stream_min; int stream_piece;
 	int spec;
 	int last_rows;                 // 1: the last process call ran kern_rows
 	int rows_fe_warps, rows_be_lanes;
@@ -1591,6 +1755,12 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		const int fir_on = (params->downsample_passes > 0 && params->comp_fir_size == 9) ? 1 : 0;
 		h->kern_rows = (spec == 1 && !getenv("RXB200_FM_NOROWS")) ? pick_rows_kernel(params->downsample_passes, fir_on) : nullptr;
 		h->kern_segs = (spec == 1 && !getenv("RXB200_FM_NOSPLIT")) ? pick_segs_kernel(params->downsample_passes, params->downsample, params->deemph) : nullptr;
+		// stream path (front kernel + back kernel): the wbfm shape without decimating passes, de-emphasis on
+#ifndef RXB_QUICK
+		h->kern_front = (spec == 1 && params->downsample_passes == 0 && params->deemph && !getenv("RXB200_FM_NOSTREAM")) ? pick_kernel(0, 4, h->threads) : nullptr;
+#endif
+		h->stream_min = getenv("RXB200_FM_STREAM_MIN") ? (size_t)atoll(getenv("RXB200_FM_STREAM_MIN")) : (size_t)-1;   // -1: derived per call
+		h->stream_piece = getenv("RXB200_FM_STREAM_PIECE") ? atoi(getenv("RXB200_FM_STREAM_PIECE")) : 0;
 		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = ROWS_BE_LANES;
 		h->env_seg = getenv("RXB200_FM_SEG") ? atoll(getenv("RXB200_FM_SEG")) : 0;
 		h->env_be_lanes = getenv("RXB200_FM_BE_LANES") ? atoi(getenv("RXB200_FM_BE_LANES")) : 0;
@@ -1661,7 +1831,7 @@ extern "C" void rxb200_fm_destroy(rxb200_fm *h)
 	cudaSetDevice(h->device);
 	if (h->stream) { cudaStreamSynchronize(h->stream); }
 	cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_sync);
-	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out);
+	cudaFree(h->d_atan_lut); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_pcm);
 	cudaFree(h->d_sums); cudaFree(h->d_rdc); cudaFree(h->d_sqz); cudaFree(h->d_adc); cudaFree(h->d_lens); cudaFree(h->d_levels);
 	delete h->h_lens;
 	if (h->ev0) { cudaEventDestroy(h->ev0); }
@@ -1913,11 +2083,20 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	// front-end replay: decimated samples until cascade (6) + droop FIR (9) + discriminator (1) are exact
 	const long long dec_exact = (P ? (dv.fir_on ? 16 : 8) : 3) + (dv.post_ds > 1 ? dv.post_ds : 0);
 	const long long halo = round_up_ll(dec_exact * Dtot, G);
-	const int direct_out = (dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample && !dv.adc_on)) ? 1 : 0;
 	const long long Dpcm = Dtot * dv.post_ds;   // input samples per PCM sample
 	// back-end replay (decimated samples): de-emphasis bracket + one resampler group
 	long long wd = 0;
 	if (dv.deemph) { wd = h->tune_warm > 0 ? h->tune_warm : 16LL * p.deemph_a + 64; }
+	// Stream path: the front end of the whole call stores its PCM to global memory (SPEC 4 through the direct-output
+	// path), fm_back_kernel then runs the serial stages with pieces as long as the call allows.  In the fused kernel a
+	// piece is a lane's share of one shared-memory buffer -- at the capture rate (fm2a) 870 samples behind a 2960-step
+	// replay, and the item's front end recomputes the replay region too; here the replay is paid once per piece of
+	// a few thousand samples and the front end computes nothing twice.  Worth it from a few dozen replays of PCM per call.
+	const long long m_total = (n + Dtot - 1) / Dtot + 1;
+	const size_t stream_min = h->stream_min != (size_t)-1 ? h->stream_min : (size_t)(32 * wd * Dpcm / h->n_channels);
+	const bool stream = h->kern_front != nullptr && dv.deemph && (size_t)n >= stream_min;
+	const fm_kernel_fn kern = stream ? h->kern_front : h->kern;
+	const int direct_out = stream ? 1 : ((dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample && !dv.adc_on)) ? 1 : 0);
 	const long long W_dec = direct_out ? 0 : wd;
 	// PCM the CTA needs from before its stretch: the replay plus the resampler group in progress
 	const long long margin_dec = direct_out ? 0 : W_dec + (dv.resample ? (p.rate_out / p.rate_out2 + 2) : 0) + 2;
@@ -1970,9 +2149,9 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 			return RXB200_EUNSUPPORTED;
 		}
 	}
-	RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	RXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 1;
-	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, T, smem));
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	if (!sf_forced) {
 		// tail balancing: work items are handed out to n_sm*per_sm resident CTAs; prefer a slightly shorter
@@ -2004,10 +2183,29 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 			Sf = pick;
 			geometry(Sf);
 		}
-		RXB_CUDA(cudaFuncSetAttribute(h->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		RXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
 	const size_t total_work = (size_t)n_cta * h->n_channels;
-	const size_t need_sync = 4 + 4 * total_work;
+	// stream path: geometry of the back kernel -- BACK_T pieces per item, `piece` PCM samples each
+	long long piece = 0, span = 0, n_cta_b = 0, pstride = 0;
+	if (stream) {
+		const long long lanes_target = (long long)h->n_sm * 3 * BACK_T;      // three resident CTAs per SM (shared-memory windows)
+		piece = h->stream_piece > 0 ? h->stream_piece : (m_total * h->n_channels + lanes_target - 1) / lanes_target;
+		if (h->stream_piece <= 0 && piece < wd / 2) { piece = wd / 2; }
+		if (piece < 64) { piece = 64; }
+		if (piece * BACK_T * Dpcm > 0x40000000LL) { piece = 0x40000000LL / (BACK_T * Dpcm); }
+		span = piece * BACK_T * Dpcm;
+		n_cta_b = (n + span - 1) / span;
+		pstride = (m_total + WIN_SAMPLES + 64 + 7) & ~7LL;      // a window may reach past the last sample
+		const size_t need = (size_t)pstride * h->n_channels;
+		if (need > h->d_pcm_cap) {
+			cudaFree(h->d_pcm); h->d_pcm = nullptr; h->d_pcm_cap = 0;
+			RXB_CUDA(cudaMalloc(&h->d_pcm, need * sizeof(int16_t)));
+			h->d_pcm_cap = need;
+		}
+	}
+	const size_t total_back = (size_t)n_cta_b * h->n_channels;
+	const size_t need_sync = 4 + 4 * (total_work > total_back ? total_work : total_back);
 	if (need_sync > h->sync_cap) {
 		cudaFree(h->d_sync); h->d_sync = nullptr; h->sync_cap = 0;
 		RXB_CUDA(cudaMalloc(&h->d_sync, need_sync * sizeof(int)));
@@ -2016,6 +2214,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	FmCall k;
 	memset(&k, 0, sizeof k);
 	k.in = d_in; k.out = d_out; k.n = n; k.out_stride = (long long)out_stride; k.chunk = (int)(chunk_int16 / 2);
+	if (stream) { k.out = h->d_pcm; k.out_stride = pstride; }
 	k.n_ch = h->n_channels; k.Sf = (int)Sf; k.halo = (int)halo; k.n_extra = (int)n_extra; k.n_own = (int)n_own;
 	k.n_cta = (int)n_cta; k.W_dec = (int)W_dec; k.pcm_cap = (int)pcm_cap; k.direct_out = direct_out;
 	{
@@ -2034,7 +2233,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	k.ticket = h->d_sync; k.fix_count = h->d_sync + 1; k.pub = h->d_sync + 4;
 	const int n_chunks = (int)((n + k.chunk - 1) / k.chunk);
 	k.n_chunks = n_chunks;
-	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->kern, T, smem));
+	RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
 	if (per_sm < 1) { per_sm = 1; }
 	size_t blocks = (size_t)h->n_sm * per_sm;
 	if (blocks > total_work) { blocks = total_work; }
@@ -2043,7 +2242,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		k.reduce_mode = reduce_mode; k.one = 1;
 		RXB_CUDA(cudaMemsetAsync(h->d_sync, 0, need_sync * sizeof(int), h->stream));
 		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev0, h->stream)); }
-		h->kern<<<(unsigned)blocks, T, smem, h->stream>>>(dv, k);
+		kern<<<(unsigned)blocks, T, smem, h->stream>>>(dv, k);
 		RXB_CUDA(cudaGetLastError());
 		if (reduce_mode == 0) { RXB_CUDA(cudaEventRecord(h->ev1, h->stream)); }
 		launches++;
@@ -2118,9 +2317,27 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		int rc2 = run_fused(0);
 		if (rc2 != RXB200_OK) { return rc2; }
 	}
+	if (stream) {
+		FmCall kb = k;
+		kb.out = d_out; kb.out_stride = (long long)out_stride; kb.direct_out = 0;
+		kb.pcm_g = h->d_pcm; kb.pcm_g_stride = pstride;
+		kb.n_extra = 0; kb.n_own = 1; kb.Sf = (int)span; kb.n_cta = (int)n_cta_b; kb.W_dec = (int)wd; kb.be_lanes = BACK_T;
+		kb.ticket = h->d_sync + 2;
+		const size_t smem_b = (size_t)(BACK_T / 32) * 32 * WIN_ROW_WORDS * sizeof(uint32_t);
+		RXB_CUDA(cudaFuncSetAttribute(fm_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+		int per_b = 1;
+		RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, fm_back_kernel, BACK_T, smem_b));
+		if (per_b < 1) { per_b = 1; }
+		size_t blocks_b = (size_t)h->n_sm * per_b;
+		if (blocks_b > total_back) { blocks_b = total_back; }
+		fm_back_kernel<<<(unsigned)blocks_b, BACK_T, smem_b, h->stream>>>(dv, kb);
+		RXB_CUDA(cudaGetLastError());
+		RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
+		launches++;
+	}
 	h->cur ^= 1;
 	h->stats.launches = launches; h->stats.segments = (int)(total_work * T); h->stats.segment_len = (int)Sf;
-	h->stats.warmup_len = (int)(W_dec * Dtot); h->stats.fixup_segments = -1; h->stats.kernel_kind = 0;
+	h->stats.warmup_len = (int)((stream ? wd : W_dec) * Dtot); h->stats.fixup_segments = -1; h->stats.kernel_kind = stream ? 3 : 0;
 	return RXB200_OK;
 }
 

@@ -210,6 +210,33 @@ def test_split_kernel_with_segment_front_end(name, seg, port, monkeypatch):
     d.close()
 
 
+@pytest.mark.parametrize("piece", [0, 64, 300])
+@pytest.mark.parametrize("name", ["cfg2A", "zeros_deemph", "wbfm_deemph_quiet"])
+def test_stream_path_front_kernel_then_back_kernel(name, piece, port, monkeypatch):
+    """The undecimated wbfm shape on long calls runs two kernels: the front end of the whole call (PCM to global memory),
+    then fm_back_kernel with pieces as long as the call allows.  RXB200_FM_STREAM_MIN=0 selects the path for a test-sized
+    call; RXB200_FM_STREAM_PIECE sets the piece length (several items per channel, look-back between them)."""
+    names = [c.name for c in fm_cases()]
+    if name not in names:
+        pytest.skip("no such case")
+    monkeypatch.setenv("RXB200_FM_STREAM_MIN", "0")
+    if piece:
+        monkeypatch.setenv("RXB200_FM_STREAM_PIECE", str(piece))
+    case = next(c for c in fm_cases() if c.name == name)
+    x = case.make_input()
+    want = port.fm_run(case.params, x, case.chunk_int16)
+    d = fm.FmDemod(case.params)
+    got = d.full_demod(x, case.chunk_int16)
+    _compare(case, got, want)
+    assert d.stats()["kernel_kind"] == 3
+    # streaming: the carry written by the two kernels feeds the next call
+    d.reset()
+    cut = (x.size // 3 // case.chunk_int16) * case.chunk_int16 or case.chunk_int16
+    got2 = np.concatenate([d.full_demod(x[:cut], case.chunk_int16), d.full_demod(x[cut:], case.chunk_int16)])
+    _compare(case, got2, want)
+    d.close()
+
+
 def test_row_kernel_is_the_one_that_runs(port):
     case = next(c for c in fm_cases() if c.name == "cfg2B")
     d = fm.FmDemod(case.params)
