@@ -3,7 +3,7 @@
 OUT=gpurun_out/r2r; mkdir -p $OUT
 exec > $OUT/session.log 2>&1
 date
-timeout 900 python -m pytest tests/test_fm_gpu.py tests/test_fm_fuzz_gpu.py tests/test_golden_gpu.py tests/test_full_size_gpu.py tests/test_dropin.py -m gpu -x -q > $OUT/tests.txt 2>&1
+timeout 900 python -m pytest tests/test_fm_gpu.py tests/test_fuzz_gpu.py tests/test_golden_gpu.py tests/test_full_size_gpu.py tests/test_dropin.py -m gpu -x -q > $OUT/tests.txt 2>&1
 echo "tests rc=$?"; tail -4 $OUT/tests.txt
 run() { # name, env...
 	local name=$1; shift
