@@ -192,9 +192,43 @@ __device__ __forceinline__ void front_store(const FrontState<P, SPEC> &s, uint32
 // B (lane = v + B, |v| <= B) the lane sum is < 64 B <= 32768, so no carry crosses lanes, and
 // (sum + 32 B) >> 4 == (sum >> 4) + 2 B exactly: the output lanes are biased by 2 B.  The int16
 // store of the reference never wraps here because |v| <= 128 << level after the 8-bit-range scale.
+// Pipe balance (HB_MAD): the integer adder/shifter pipe and the multiplier pipe each take a warp instruction every other
+// cycle; the row loop has ~550 instructions for the first against ~380 for the second, so the tap set's three adds are
+// the cheapest thing to move: as a chain of multiply-adds (inline PTX: the compiler would factor the sums out again)
+// the tap set costs four (HB_MAD 1) or five (HB_MAD 2: the last add through a multiplier the compiler cannot see
+// through, c_one == 1 in constant memory) multiplier-pipe instructions and one or none on the adder pipe.
+#ifndef HB_MAD
+#define HB_MAD 0
+#endif
+__constant__ int c_one = 1;
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+template <int M>
+__device__ __forceinline__ uint32_t mad_imm(uint32_t a, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "n"(M), "r"(c));
+	return d;
+}
 __device__ __forceinline__ uint32_t hb_tap(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f)
 {
+#if HB_MAD == 0
 	uint32_t s = a + f + (b + e) * 5u + (c + d) * 10u;
+#else
+	uint32_t s = mad_imm<5>(b, a);
+	s = mad_imm<5>(e, s);
+	s = mad_imm<10>(c, s);
+	s = mad_imm<10>(d, s);
+#if HB_MAD == 2
+	s = mad_u32(f, (uint32_t)c_one, s);
+#else
+	s += f;
+#endif
+#endif
 	return (s >> 4) & 0x0FFF0FFFu;
 }
 
@@ -507,7 +541,14 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 __device__ __forceinline__ void scale_rot(uint32_t w, int pos, bool rotate, int &ri, int &rq, int dci = 0, int dcq = 0)
 {
 	// dc_block_raw_filter subtracts the chunk's running mean between the scale and the rotation (:850-857)
-	int xi = wrap16(scale_cs16(lo16(w)) - dci), xq = wrap16(scale_cs16(hi16(w)) - dcq);
+	// SC_DP: the two halves of the CS16 word leave it through a two-way dot product (dp2a: I * 1 + Q * 0) instead of a
+	// byte permute / shift -- the same value from the other integer pipe (see HB_MAD)
+#ifndef SC_DP
+#define SC_DP 0
+#endif
+	const int wi16 = (SC_DP == 1 || SC_DP == 3) ? __dp2a_lo((int)w, 0x0001, 0) : lo16(w);
+	const int wq16 = (SC_DP == 1 || SC_DP == 2) ? __dp2a_lo((int)w, 0x0100, 0) : hi16(w);
+	int xi = wrap16(scale_cs16(wi16) - dci), xq = wrap16(scale_cs16(wq16) - dcq);
 	if (!rotate) { pos = 0; }
 	switch (pos & 3) {
 	case 1: ri = -xq; rq = xi; break;
@@ -621,7 +662,12 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 		for (int j = 0; j < 8; j++) {
 			int xi, xq;
 			scale_rot(v[j], j, rot, xi, xq, e.rdc_i, e.rdc_q);
-			s.box_i += xi; s.box_q += xq;
+			// BX_MAD: the running sums through the multiplier pipe (x * 1 + sum, see HB_MAD); 2: the I sum only
+#ifndef BX_MAD
+#define BX_MAD 0
+#endif
+			if (BX_MAD >= 1) { s.box_i = (int)mad_u32((uint32_t)xi, (uint32_t)c_one, (uint32_t)s.box_i); } else { s.box_i += xi; }
+			if (BX_MAD == 1) { s.box_q = (int)mad_u32((uint32_t)xq, (uint32_t)c_one, (uint32_t)s.box_q); } else { s.box_q += xq; }
 			if (++s.box_n >= c.D) {
 				int di = wrap16(s.box_i), dq = wrap16(s.box_q);
 				s.box_i = 0; s.box_q = 0; s.box_n = 0;
@@ -670,35 +716,78 @@ __device__ __forceinline__ int deemph_fast(int avg, int x, int xb, unsigned magi
 template <int PAD>
 __device__ __forceinline__ int pcm_load(const int16_t *pcm_s, int m) { return (int)pcm_s[pcm_phys<PAD>(m)]; }
 
+// The de-emphasis step as the replay / output loops see it: a state, a sample as loaded from the PCM buffer, a step.
+// Integer form: deemph_fast above.  FP32 form (odd a): the reference's avg += trunc((d +- a/2) / a) is d / a rounded
+// to the nearest integer, and an odd a has no ties.  Keep the state as the float U = 2^23 + 32768 + avg (an integer
+// below 2^24, so one ulp is exactly 1) and build the sample X = 2^23 + 32768 + x straight from its 16 bits
+// ((x ^ 0x8000) | 0x4B000000).  Then d = X - U is exact and fma(d, fl(1/a), U), rounded to nearest by the hardware,
+// IS U + rn(d / a): the product's error (< |d| 2^-24 / a) is far below the distance of d / a from a half-integer
+// (>= 1 / (2a)).  Two full-rate FP32 instructions on an 8-cycle dependency instead of subtract, 64-bit multiply-high
+// and add -- the multiply-high (IMAD.HI) is what the back kernel's warps were waiting for.  Bit-exact by construction
+// and by the parity suite; even a (ties round away from zero in the reference) keeps the integer form.
+#ifndef DEEMPH_F32
+#define DEEMPH_F32 1
+#endif
+#define DF_BIAS 0x4B008000
+template <bool EVEN, bool F32>
+struct DeemphOp {
+	typedef int State;
+	typedef int Sample;
+	int bias, K;
+	unsigned magic;
+	__device__ __forceinline__ DeemphOp(const FmDev &c) : bias(c.a_half + c.a_K * c.a), K(c.a_K), magic(c.a_magic) {}
+	__device__ __forceinline__ State enter(int avg) const { return avg; }
+	__device__ __forceinline__ int value(State s) const { return s; }
+	__device__ __forceinline__ Sample load(const int16_t *p) const { return (int)*p; }
+	__device__ __forceinline__ State step(State s, Sample x) const { return deemph_fast<EVEN>(s, x, x + bias, magic, K); }
+};
+template <>
+struct DeemphOp<false, true> {
+	typedef float State;
+	typedef float Sample;
+	float inv_a;
+	__device__ __forceinline__ DeemphOp(const FmDev &c) : inv_a(1.0f / (float)c.a) {}
+	__device__ __forceinline__ State enter(int avg) const { return __int_as_float(DF_BIAS + avg); }
+	__device__ __forceinline__ int value(State s) const { return __float_as_int(s) - DF_BIAS; }
+	__device__ __forceinline__ Sample load(const int16_t *p) const
+	{
+		return __int_as_float((int)(((unsigned)*reinterpret_cast<const uint16_t *>(p) ^ 0x8000u) | 0x4B000000u));
+	}
+	__device__ __forceinline__ State step(State s, Sample x) const { return __fmaf_rn(__fsub_rn(x, s), inv_a, s); }
+};
+template <bool EVEN>
+struct Deemph : DeemphOp<EVEN, (!EVEN && DEEMPH_F32 != 0)> {
+	__device__ __forceinline__ Deemph(const FmDev &c) : DeemphOp<EVEN, (!EVEN && DEEMPH_F32 != 0)>(c) {}
+};
+
 // deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a
 // piece).  The two trajectories are independent, the next sample is fetched one step ahead.
 template <bool EVEN, int PAD>
 __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
 {
 	if (m >= m_end) { return; }
-	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
-	const unsigned magic = c.a_magic;
 	if (c.a_use_magic) {
+		const Deemph<EVEN> dm(c);
+		typename Deemph<EVEN>::State l = dm.enter(lo), h = dm.enter(hi);
 		// quads never straddle a padding step (128 is a multiple of 4): one address, four immediate offsets
 		for (; (m & 3) != 0 && m < m_end; m++) {
-			const int x = pcm_load<PAD>(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
-			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+			const typename Deemph<EVEN>::Sample x = dm.load(pcm_s + pcm_phys<PAD>(m));
+			l = dm.step(l, x); h = dm.step(h, x);
 		}
 #pragma unroll 2
 		for (; m + 4 <= m_end; m += 4) {
 			const int16_t *q = pcm_s + pcm_phys<PAD>(m);
-			const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
-			lo = deemph_fast<EVEN>(lo, x0, x0 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x0, x0 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x1, x1 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x1, x1 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x2, x2 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x2, x2 + bias, magic, K);
-			lo = deemph_fast<EVEN>(lo, x3, x3 + bias, magic, K); hi = deemph_fast<EVEN>(hi, x3, x3 + bias, magic, K);
+			const typename Deemph<EVEN>::Sample x0 = dm.load(q), x1 = dm.load(q + 1), x2 = dm.load(q + 2), x3 = dm.load(q + 3);
+			l = dm.step(l, x0); h = dm.step(h, x0);
+			l = dm.step(l, x1); h = dm.step(h, x1);
+			l = dm.step(l, x2); h = dm.step(h, x2);
+			l = dm.step(l, x3); h = dm.step(h, x3);
 		}
 		for (; m < m_end; m++) {
-			const int x = pcm_load<PAD>(pcm_s, m);
-			lo = deemph_fast<EVEN>(lo, x, x + bias, magic, K);
-			hi = deemph_fast<EVEN>(hi, x, x + bias, magic, K);
+			const typename Deemph<EVEN>::Sample x = dm.load(pcm_s + pcm_phys<PAD>(m));
+			l = dm.step(l, x); h = dm.step(h, x);
 		}
+		lo = dm.value(l); hi = dm.value(h);
 	} else {
 		for (; m < m_end; m++) {
 			const int x = pcm_load<PAD>(pcm_s, m);
@@ -769,39 +858,59 @@ template <bool EVEN, int PAD, int LF>
 __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t *pcm_s, int16_t *__restrict__ out, int n_out,
                                                   int &m, int &avg, int acc, int &phase_io)
 {
-	const int bias = c.a_half + c.a_K * c.a, K = c.a_K;
-	const unsigned magic = c.a_magic;
+	const Deemph<EVEN> de(c);
+	typedef typename Deemph<EVEN>::Sample Smp;
 	int phase = phase_io;
 	const int lf = LF > 0 ? LF : c.lpr_div, slow = c.slow, fast = c.fast;
 	const int dm = c.lpr_m, dsh = c.lpr_s, dadd = c.lpr_add;
 	const int16_t *p = pcm_s + pcm_phys<PAD>(m);        // PAD == 0 here: consecutive samples are consecutive entries
-	int a = avg, mm = m;
+	typename Deemph<EVEN>::State a = de.enter(avg);
+	int mm = m;
 	int16_t *op = out;
 	for (int n = 0; n < n_out; n++) {
 		int ph = phase + lf * slow;
 		const bool extra = ph < fast;
 		if (extra) { ph += slow; }
 		phase = ph - fast;
+		// (the reference's int16 store of avg changes nothing: a step moves avg towards x and never past it, so avg stays
+		// inside the int16 range of the inputs and of the carried state -- no wrap16 on the accumulate)
 		if constexpr (LF > 0 && PAD == 0) {
 #pragma unroll
 			for (int j = 0; j < LF; j++) {
-				const int x = p[j];
-				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
-				acc += wrap16(a);
+				const Smp x = de.load(p + j);
+				a = de.step(a, x);
+				acc += de.value(a);
 			}
 			if (extra) {
-				const int x = p[LF];
-				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
-				acc += wrap16(a);
+				const Smp x = de.load(p + LF);
+				a = de.step(a, x);
+				acc += de.value(a);
 			}
 			p += LF + (extra ? 1 : 0);
 			mm += LF + (extra ? 1 : 0);
+		} else if constexpr (PAD == 0) {
+			// any ratio (the undecimated wbfm shape has 50 samples per output): quads, then the rest
+			const int len = lf + (extra ? 1 : 0);
+			int j = 0;
+			for (; j + 4 <= len; j += 4) {
+				const Smp x0 = de.load(p), x1 = de.load(p + 1), x2 = de.load(p + 2), x3 = de.load(p + 3);
+				a = de.step(a, x0); acc += de.value(a);
+				a = de.step(a, x1); acc += de.value(a);
+				a = de.step(a, x2); acc += de.value(a);
+				a = de.step(a, x3); acc += de.value(a);
+				p += 4;
+			}
+			for (; j < len; j++) {
+				const Smp x = de.load(p++);
+				a = de.step(a, x); acc += de.value(a);
+			}
+			mm += len;
 		} else {
 			const int len = lf + (extra ? 1 : 0);
 			for (int j = 0; j < len; j++) {
-				const int x = pcm_load<PAD>(pcm_s, mm);
-				a = deemph_fast<EVEN>(a, x, x + bias, magic, K);
-				acc += wrap16(a);
+				const Smp x = de.load(pcm_s + pcm_phys<PAD>(mm));
+				a = de.step(a, x);
+				acc += de.value(a);
 				mm++;
 			}
 		}
@@ -812,7 +921,7 @@ __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t 
 		*op++ = (int16_t)q;
 		acc = 0;
 	}
-	m = mm; avg = a; phase_io = phase;
+	m = mm; avg = de.value(a); phase_io = phase;
 }
 
 template <bool EVEN, int PAD>
@@ -856,67 +965,161 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 // A lane of the back kernel walks its own piece of the call's PCM: read straight from global memory that is one 2-byte
 // load per step to 32 different lines per warp -- 32 trips through the L1 tag stage per step, which at one PCM sample per
 // input sample (fm2a) costs more than the arithmetic.  Instead the warp copies, for each of its lanes in turn, the next
-// WIN_SAMPLES of that lane's piece with coalesced 4-byte loads into a row of shared memory (one line per load), and the
-// lanes then run the unchanged replay / output loops out of their rows.  Odd row stride: lanes reading the same offset
-// of their rows hit 32 different banks.
-#define WIN_SAMPLES 256
-#define WIN_ROW_WORDS (WIN_SAMPLES / 2 + 1)
+// WS samples of that lane's piece with coalesced 4-byte asynchronous copies (cp.async: global -> shared without a trip
+// through registers) into a row of shared memory, and the lanes then run the unchanged replay / output loops out of
+// their rows.  Two buffers per warp: the copies of the NEXT window are in flight while the lanes work through the
+// current one (the first ncu pass of the synchronous version had the warps waiting for their own fills 29 % of the time
+// and idle at the item barriers behind them another 29 %).  Where a lane's next window starts is known before the
+// current one is processed: a replay consumes the whole window, and the samples n resampler groups consume depend on
+// the phase alone.  Odd row stride: lanes reading the same offset of their rows hit 32 different banks.
+template <int WS>
 struct LaneWin {
+	static constexpr int ROW = WS / 2 + 1;      // words per row
+	static constexpr int BUF = 32 * ROW;        // words per buffer (one row per lane)
 	const int16_t *g;         // the channel's PCM in global memory
-	uint32_t *rows;           // this warp's 32 rows
+	uint32_t *rows;           // this warp's two buffers
 	int lane;
 };
-// all 32 lanes: lane l's row <- g[base_l .. base_l + WIN_SAMPLES), base_l even
-__device__ __forceinline__ void win_fill(const LaneWin &w, int base)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
 {
-	constexpr int NV = WIN_SAMPLES / 64;
-#pragma unroll 4
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// all 32 lanes: lane l's row of buffer `buf` <- g[base_l .. base_l + WS), base_l even; one commit group per call
+template <int WS>
+__device__ __forceinline__ void win_issue(const LaneWin<WS> &w, int buf, int base)
+{
+	constexpr int NV = WS / 64;
+	const uint32_t dst0 = smem_u32(w.rows + buf * LaneWin<WS>::BUF + w.lane);
+	// fully unrolled: the destination of every copy is dst0 plus a compile-time offset, a row costs one shuffle, one
+	// address and its copies
+	const char *gl = reinterpret_cast<const char *>(w.g) + 4 * w.lane;      // this lane's word of every row
+#pragma unroll
 	for (int l = 0; l < 32; l++) {
-		const int b = __shfl_sync(0xffffffffu, base, l);
-		const uint32_t *src = reinterpret_cast<const uint32_t *>(w.g + b) + w.lane;
-		uint32_t *dst = w.rows + l * WIN_ROW_WORDS + w.lane;
-		uint32_t t[NV];
+		const unsigned b = (unsigned)__shfl_sync(0xffffffffu, base, l);       // bases are never negative: one 32 x 32 -> 64 multiply-add
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(gl + 2ull * b);
+		const uint32_t dst = dst0 + (uint32_t)(l * LaneWin<WS>::ROW * 4);
 #pragma unroll
-		for (int i = 0; i < NV; i++) { t[i] = __ldg(src + 32 * i); }
-#pragma unroll
-		for (int i = 0; i < NV; i++) { dst[32 * i] = t[i]; }
+		for (int i = 0; i < NV; i++) { cp_async4(dst + 128u * i, src + 32 * i); }
 	}
+	cp_async_commit();
 }
-// back_replay over PCM [m, m_end) through windows; every lane of the warp takes part (an empty range for lanes with nothing to do)
-template <bool EVEN>
-__device__ __forceinline__ void win_replay(const FmDev &c, const LaneWin &w, int m, int m_end, int &lo, int &hi)
+// back_replay over PCM [m, m_end) through windows; every lane of the warp takes part (an empty range for lanes with
+// nothing to do: they keep re-reading the window they stand on)
+template <bool EVEN, int WS>
+__device__ __forceinline__ void win_replay(const FmDev &c, const LaneWin<WS> &w, int m, int m_end, int &lo, int &hi)
 {
-	const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + w.lane * WIN_ROW_WORDS);
-	while (__any_sync(0xffffffffu, m < m_end)) {
-		const int base = m & ~1;
-		win_fill(w, base);
+	if (!__any_sync(0xffffffffu, m < m_end)) { return; }
+	int base = m & ~1, buf = 0;
+	__syncwarp();
+	win_issue(w, 0, base);
+	for (;;) {
+		const int e = m_end < base + WS ? m_end : base + WS;
+		const int m_next = m < e ? e : m;
+		const bool more = __any_sync(0xffffffffu, m_next < m_end);
+		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
-		const int e = m_end < base + WIN_SAMPLES ? m_end : base + WIN_SAMPLES;
-		if (m < e) { back_replay<EVEN, 0>(c, row - base, m, e, lo, hi); m = e; }
-		__syncwarp();
+		const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW);
+		if (m < e) { back_replay<EVEN, 0>(c, row - base, m, e, lo, hi); }
+		__syncwarp();                          // every lane is through with this buffer before the next fill but one lands in it
+		if (!more) { break; }
+		m = m_next; base = m_next & ~1; buf ^= 1;
 	}
 }
-// back_outputs_lean for `remaining` outputs through windows: per window as many whole resampler groups as it holds
-template <bool EVEN>
-__device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin &w, int16_t *__restrict__ op, int remaining, int &m, int &avg,
+// back_probe over PCM [m, m_end) through windows (an open bracket's piece); returns the lane's `moved` word
+template <bool EVEN, int WS>
+__device__ __forceinline__ int win_probe(const FmDev &c, const LaneWin<WS> &w, int m, int m_end, int &lo, int &hi)
+{
+	int moved = 0;
+	if (!__any_sync(0xffffffffu, m < m_end)) { return moved; }
+	int base = m & ~1, buf = 0;
+	__syncwarp();
+	win_issue(w, 0, base);
+	for (;;) {
+		const int e = m_end < base + WS ? m_end : base + WS;
+		const int m_next = m < e ? e : m;
+		const bool more = __any_sync(0xffffffffu, m_next < m_end);
+		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+		__syncwarp();
+		const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW);
+		if (m < e) { moved |= back_probe<EVEN, 0>(c, row - base, m, e, lo, hi); }
+		__syncwarp();
+		if (!more) { break; }
+		m = m_next; base = m_next & ~1; buf ^= 1;
+	}
+	return moved;
+}
+// The lean output loop (back_outputs_lean: reciprocal de-emphasis, resampler on, regular groups, no audio DC block)
+// through windows.  Driven by samples, not by groups: a window is used to its last sample and a resampler group may
+// straddle two windows (accumulator, phase and the samples the group still needs are lane state), so the window size
+// is independent of the rate ratio.  The lane stops with the sample that completes its last output -- known up front:
+// n groups end with the first sample that takes the running phase to n * fast (low_pass_real, src/rtl_fm.c:396-407).
+template <bool EVEN, int WS>
+__device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin<WS> &w, int16_t *__restrict__ op, int remaining, int &m, int &avg,
                                             int acc, int phase)
 {
-	const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + w.lane * WIN_ROW_WORDS);
-	const int lf1 = c.lpr_div + 1;
-	while (__any_sync(0xffffffffu, remaining > 0)) {
-		const int base = m & ~1;
-		win_fill(w, base);
+	if (!__any_sync(0xffffffffu, remaining > 0)) { return; }
+	const Deemph<EVEN> de(c);
+	typedef typename Deemph<EVEN>::Sample Smp;
+	const int lf = c.lpr_div, slow = c.slow, fast = c.fast;
+	const int dm = c.lpr_m, dsh = c.lpr_s, dadd = c.lpr_add;
+	typename Deemph<EVEN>::State a = de.enter(avg);
+	int mm = m;
+	const int m_stop = remaining > 0 ? mm + (int)(((long long)remaining * fast - phase + slow - 1) / slow) : mm;
+	int g_left = 0;                            // samples the group in progress still needs
+	if (remaining > 0) {
+		int ph = phase + lf * slow;
+		const bool extra = ph < fast;
+		if (extra) { ph += slow; }
+		phase = ph - fast; g_left = lf + (extra ? 1 : 0);
+	}
+	int base = mm & ~1, buf = 0;
+	__syncwarp();
+	win_issue(w, 0, base);
+	for (;;) {
+		const int e = m_stop < base + WS ? m_stop : base + WS;
+		const int m_next = mm < e ? e : mm;
+		const bool more = __any_sync(0xffffffffu, m_next < m_stop);
+		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
-		int n = (base + WIN_SAMPLES - m) / lf1;
-		if (n > remaining) { n = remaining; }
-		if (n > 0) {
-			if (c.lpr_div == 6) { back_outputs_lean<EVEN, 0, 6>(c, row - base, op, n, m, avg, acc, phase); }
-			else if (c.lpr_div == 5) { back_outputs_lean<EVEN, 0, 5>(c, row - base, op, n, m, avg, acc, phase); }
-			else { back_outputs_lean<EVEN, 0, 0>(c, row - base, op, n, m, avg, acc, phase); }
-			op += n; remaining -= n; acc = 0;
+		const int16_t *p = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW) + (mm - base);
+		while (mm < e) {
+			int run = e - mm;
+			if (run > g_left) { run = g_left; }
+			int j = 0;
+			for (; j + 4 <= run; j += 4) {
+				const Smp x0 = de.load(p), x1 = de.load(p + 1), x2 = de.load(p + 2), x3 = de.load(p + 3);
+				a = de.step(a, x0); acc += de.value(a);
+				a = de.step(a, x1); acc += de.value(a);
+				a = de.step(a, x2); acc += de.value(a);
+				a = de.step(a, x3); acc += de.value(a);
+				p += 4;
+			}
+			for (; j < run; j++) {
+				const Smp x = de.load(p++);
+				a = de.step(a, x); acc += de.value(a);
+			}
+			mm += run; g_left -= run;
+			if (g_left == 0) {
+				int q = __mulhi(acc, dm);
+				if (dadd) { q += acc; }
+				q >>= dsh;
+				q += (int)((unsigned)q >> 31);
+				*op++ = (int16_t)q;
+				acc = 0;
+				int ph = phase + lf * slow;
+				const bool extra = ph < fast;
+				if (extra) { ph += slow; }
+				phase = ph - fast; g_left = lf + (extra ? 1 : 0);
+			}
 		}
 		__syncwarp();
+		if (!more) { break; }
+		base = m_next & ~1; buf ^= 1;
 	}
+	m = mm; avg = de.value(a);
 }
 
 // Runs blocks [t, t_end) of one segment; chunk bookkeeping shared by the replay and the owned part.
@@ -1107,15 +1310,15 @@ __device__ __forceinline__ void run_piece(const FmDev &c, const int16_t *pcm_s, 
 }
 
 // run_piece through windows (fm_back_kernel): every lane of the warp calls it, `run` says whether this lane has a piece to run
-__device__ __forceinline__ void run_piece_win(const FmDev &c, const LaneWin &w, int16_t *__restrict__ out, const Piece &p,
+template <int WS>
+__device__ __forceinline__ void run_piece_win(const FmDev &c, const LaneWin<WS> &w, int16_t *__restrict__ out, const Piece &p,
                                               int &m_run, int &avg, AdcCtx *ax, bool store, bool run)
 {
-	const bool lean = run && c.deemph && c.a_use_magic && c.resample && c.lpr_ok && p.ph0 < c.slow && ax == nullptr && store &&
-	                  2 * (c.lpr_div + 1) <= WIN_SAMPLES;
+	const bool lean = run && c.deemph && c.a_use_magic && c.resample && c.lpr_ok && p.ph0 < c.slow && ax == nullptr && store;
 	int m = p.ga, a = avg;
 	const int n_out = lean ? (int)(p.ob - p.oa) : 0;
-	if (c.a_even) { win_outputs<true>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
-	else { win_outputs<false>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
+	if (c.a_even) { win_outputs<true, WS>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
+	else { win_outputs<false, WS>(c, w, out + p.oa, n_out, m, a, p.acc0, p.ph0); }
 	if (lean) { m_run = m; avg = a; }
 	else if (run) { run_piece<0>(c, w.g, out, p, m_run, avg, ax, store); }      // any other shape: straight from global memory
 }
@@ -1124,14 +1327,15 @@ __device__ __forceinline__ void run_piece_win(const FmDev &c, const LaneWin &w, 
 #define BAR_BE 1                 // named barrier of the back-end warps (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// WIN: the PCM is the call's global array and replay / outputs go through per-lane windows in `win_rows` (fm_back_kernel;
-// whole warps call, every lane takes part in the window fills)
-template <int SPEC, int PAD, bool WIN = false>
+// WS > 0: the PCM is the call's global array and replay / outputs go through per-lane windows of WS samples in `win_rows`
+// (fm_back_kernel; whole warps call, every lane takes part in the window fills)
+template <int SPEC, int PAD, int WS = 0>
 __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const Item &it, int work, int q, int lanes,
                                           const int16_t *pcm_s, int *s_avg, int *s_mrun, unsigned char *s_ok, int *s_start,
                                           uint32_t *win_rows = nullptr)
 {
-	LaneWin lw;
+	constexpr bool WIN = WS > 0;
+	LaneWin<WIN ? WS : 64> lw;
 	lw.g = pcm_s; lw.rows = win_rows; lw.lane = q & 31;
 	const uint32_t *carry = k.carry_in + (size_t)it.ch * k.state_words;
 	int16_t *__restrict__ out = k.out + (size_t)it.ch * (size_t)k.out_stride;
@@ -1171,15 +1375,25 @@ __device__ __forceinline__ void back_item(const FmDev &c, const FmCall &k, const
 		if (!replayed && need && c.deemph) {
 			if (c.a_even) { back_replay<true, PAD>(c, pcm_s, ws, p.ga, lo, hi); } else { back_replay<false, PAD>(c, pcm_s, ws, p.ga, lo, hi); }
 		}
+		// Open bracket (quiet input: the rounding IIR has a dead zone).  Summarise what the piece does to
+		// ANY state in [lo, hi] by running both ends through it: if they meet, the end state is exact
+		// whatever the start was; if neither ever moves, no state in between moves either (the fixed
+		// points of one step form an interval), so the piece passes its start state through.
+		const bool open = need && c.deemph && lo != hi;
+		const int ge = (open && active) ? (int)(group_start(c, p.ob, it.phase0) - it.m_lo) : p.ga;
+		int moved = 0;
+		bool probed = false;
+		if constexpr (WIN) {
+			if (c.deemph && c.a_use_magic) {       // whole warp: the lanes without an open bracket pass an empty range
+				const int pe = open ? ge : p.ga;
+				moved = c.a_even ? win_probe<true>(c, lw, p.ga, pe, lo, hi) : win_probe<false>(c, lw, p.ga, pe, lo, hi);
+				probed = true;
+			}
+		}
 		if (need) {
 			avg = lo;
-			if (c.deemph && lo != hi) {
-				// Open bracket (quiet input: the rounding IIR has a dead zone).  Summarise what the piece does to
-				// ANY state in [lo, hi] by running both ends through it: if they meet, the end state is exact
-				// whatever the start was; if neither ever moves, no state in between moves either (the fixed
-				// points of one step form an interval), so the piece passes its start state through.
-				const int ge = active ? (int)(group_start(c, p.ob, it.phase0) - it.m_lo) : p.ga;
-				const int moved = c.a_even ? back_probe<true, PAD>(c, pcm_s, p.ga, ge, lo, hi) : back_probe<false, PAD>(c, pcm_s, p.ga, ge, lo, hi);
+			if (open) {
+				if (!probed) { moved = c.a_even ? back_probe<true, PAD>(c, pcm_s, p.ga, ge, lo, hi) : back_probe<false, PAD>(c, pcm_s, p.ga, ge, lo, hi); }
 				kind = (lo == hi) ? PK_MERGED : (moved == 0 ? PK_IDENT : PK_OPEN);
 				avg = lo; m_run = ge;
 			}
@@ -1322,16 +1536,18 @@ __global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3
 // at hand a piece can be as long as the launch has lanes to spare for, so the 16 a + 64 replay steps in front of every
 // piece are paid once per few thousand samples, not once per shared-memory buffer share.  Same pieces, brackets,
 // look-back and integers as back_item everywhere else.
-#define BACK_T 128
-__global__ void __launch_bounds__(BACK_T) fm_back_kernel(const FmDev c, const FmCall k)
+// WS: samples per window (two windows per lane), T: lanes (pieces) per item.
+#define BACK_T_MAX 128
+template <int WS, int T>
+__global__ void __launch_bounds__(T) fm_back_kernel(const FmDev c, const FmCall k)
 {
-	extern __shared__ __align__(16) uint32_t win_s[];      // [BACK_T / 32][32][WIN_ROW_WORDS]
+	extern __shared__ __align__(16) uint32_t win_s[];      // [T / 32][2][32][WS / 2 + 1]
 	__shared__ int s_work;
-	__shared__ int s_avg[BACK_T], s_mrun[BACK_T], s_start[BACK_T];
-	__shared__ unsigned char s_ok[BACK_T];
+	__shared__ int s_avg[T], s_mrun[T], s_start[T];
+	__shared__ unsigned char s_ok[T];
 	const int tid = threadIdx.x;
 	const int total_work = k.n_ch * k.n_cta;
-	uint32_t *rows = win_s + (size_t)(tid >> 5) * 32 * WIN_ROW_WORDS;
+	uint32_t *rows = win_s + (size_t)(tid >> 5) * 2 * LaneWin<WS>::BUF;
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) { s_work = atomicAdd(k.ticket, 1); }
@@ -1339,8 +1555,15 @@ __global__ void __launch_bounds__(BACK_T) fm_back_kernel(const FmDev c, const Fm
 		const int work = s_work;
 		if (work >= total_work) { break; }
 		const Item it = make_item(c, k, work);
-		back_item<1, 0, true>(c, k, it, work, tid, BACK_T, k.pcm_g + (size_t)it.ch * (size_t)k.pcm_g_stride, s_avg, s_mrun, s_ok, s_start, rows);
+		back_item<1, 0, WS>(c, k, it, work, tid, T, k.pcm_g + (size_t)it.ch * (size_t)k.pcm_g_stride, s_avg, s_mrun, s_ok, s_start, rows);
 	}
+}
+typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
+static fm_kernel_fn pick_back_kernel(int ws, int t)
+{
+	if (ws == 256) { return t == 32 ? fm_back_kernel<256, 32> : (t == 64 ? fm_back_kernel<256, 64> : fm_back_kernel<256, 128>); }
+	if (ws == 64) { return t == 32 ? fm_back_kernel<64, 32> : (t == 64 ? fm_back_kernel<64, 64> : fm_back_kernel<64, 128>); }
+	return t == 32 ? fm_back_kernel<128, 32> : (t == 64 ? fm_back_kernel<128, 64> : fm_back_kernel<128, 128>);
 }
 
 #include "fm_rows.cuh"
@@ -1632,7 +1855,7 @@ struct rxb200_fm {
 	fm_kernel_fn kern_segs;        // split kernel with the segment front end (null: shape not covered)
 	fm_kernel_fn kern_front;       // stream path: front end alone (SPEC 4), PCM to global memory; fm_back_kernel follows
 	int16_t *d_pcm; size_t d_pcm_cap;   // its PCM scratch, int16 elements
-	size_t stream_min; int stream_piece;
+	size_t stream_min; int stream_piece, stream_win, stream_t, stream_warm_a;
 	int spec;
 	int last_rows;                 // 1: the last process call ran kern_rows
 	int rows_fe_warps, rows_be_lanes;
@@ -1761,6 +1984,14 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 #endif
 		h->stream_min = getenv("RXB200_FM_STREAM_MIN") ? (size_t)atoll(getenv("RXB200_FM_STREAM_MIN")) : (size_t)-1;   // -1: derived per call
 		h->stream_piece = getenv("RXB200_FM_STREAM_PIECE") ? atoi(getenv("RXB200_FM_STREAM_PIECE")) : 0;
+		{
+			const int ws = getenv("RXB200_FM_STREAM_WIN") ? atoi(getenv("RXB200_FM_STREAM_WIN")) : 0;
+			h->stream_win = (ws == 64 || ws == 128 || ws == 256) ? ws : 128;
+			const int t = getenv("RXB200_FM_STREAM_T") ? atoi(getenv("RXB200_FM_STREAM_T")) : 0;
+			h->stream_t = (t == 32 || t == 64 || t == 128) ? t : 32;
+			const int wa = getenv("RXB200_FM_STREAM_WARM_A") ? atoi(getenv("RXB200_FM_STREAM_WARM_A")) : 0;
+			h->stream_warm_a = wa >= 16 ? wa : 20;
+		}
 		h->rows_fe_warps = ROWS_FE_WARPS; h->rows_be_lanes = ROWS_BE_LANES;
 		h->env_seg = getenv("RXB200_FM_SEG") ? atoll(getenv("RXB200_FM_SEG")) : 0;
 		h->env_be_lanes = getenv("RXB200_FM_BE_LANES") ? atoi(getenv("RXB200_FM_BE_LANES")) : 0;
@@ -2095,6 +2326,12 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const long long m_total = (n + Dtot - 1) / Dtot + 1;
 	const size_t stream_min = h->stream_min != (size_t)-1 ? h->stream_min : (size_t)(32 * wd * Dpcm / h->n_channels);
 	const bool stream = h->kern_front != nullptr && dv.deemph && (size_t)n >= stream_min;
+	// The bracket in front of a piece closes in two phases: the gap contracts by (1 - 1/a) per step (to 1 within ~11 a
+	// steps from the full int16 range), then the two trajectories sit one apart until a sample lands on the one residue
+	// mod a that merges them -- a geometric wait with mean a.  16 a + 64 steps leave ~0.5 % of the pieces open (measured:
+	// 280 of 56 832 on fm2a), each of which costs its item a probe and a second pass; with the stream path's long pieces
+	// four more a's of replay (e^-4: ~0.01 %) are cheaper than those stragglers.
+	if (stream && dv.deemph && h->tune_warm <= 0) { wd = (long long)h->stream_warm_a * p.deemph_a + 64; }
 	const fm_kernel_fn kern = stream ? h->kern_front : h->kern;
 	const int direct_out = stream ? 1 : ((dv.mode == RXB200_MODE_RAW || (!dv.deemph && !dv.resample && !dv.adc_on)) ? 1 : 0);
 	const long long W_dec = direct_out ? 0 : wd;
@@ -2188,15 +2425,22 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	const size_t total_work = (size_t)n_cta * h->n_channels;
 	// stream path: geometry of the back kernel -- BACK_T pieces per item, `piece` PCM samples each
 	long long piece = 0, span = 0, n_cta_b = 0, pstride = 0;
+	const int back_t = h->stream_t, back_ws = h->stream_win;
+	const fm_kernel_fn kern_back = pick_back_kernel(back_ws, back_t);
+	const size_t smem_b = (size_t)(back_t / 32) * 2 * 32 * (back_ws / 2 + 1) * sizeof(uint32_t);
+	int per_b = 1;
 	if (stream) {
-		const long long lanes_target = (long long)h->n_sm * 3 * BACK_T;      // three resident CTAs per SM (shared-memory windows)
+		RXB_CUDA(cudaFuncSetAttribute(kern_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+		RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, kern_back, back_t, smem_b));
+		if (per_b < 1) { per_b = 1; }
+		const long long lanes_target = (long long)h->n_sm * per_b * back_t;      // one piece per resident lane
 		piece = h->stream_piece > 0 ? h->stream_piece : (m_total * h->n_channels + lanes_target - 1) / lanes_target;
 		if (h->stream_piece <= 0 && piece < wd / 2) { piece = wd / 2; }
 		if (piece < 64) { piece = 64; }
-		if (piece * BACK_T * Dpcm > 0x40000000LL) { piece = 0x40000000LL / (BACK_T * Dpcm); }
-		span = piece * BACK_T * Dpcm;
+		if (piece * back_t * Dpcm > 0x40000000LL) { piece = 0x40000000LL / (back_t * Dpcm); }
+		span = piece * back_t * Dpcm;
 		n_cta_b = (n + span - 1) / span;
-		pstride = (m_total + WIN_SAMPLES + 64 + 7) & ~7LL;      // a window may reach past the last sample
+		pstride = (m_total + back_ws + 64 + 7) & ~7LL;      // a window may reach past the last sample
 		const size_t need = (size_t)pstride * h->n_channels;
 		if (need > h->d_pcm_cap) {
 			cudaFree(h->d_pcm); h->d_pcm = nullptr; h->d_pcm_cap = 0;
@@ -2321,16 +2565,11 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 		FmCall kb = k;
 		kb.out = d_out; kb.out_stride = (long long)out_stride; kb.direct_out = 0;
 		kb.pcm_g = h->d_pcm; kb.pcm_g_stride = pstride;
-		kb.n_extra = 0; kb.n_own = 1; kb.Sf = (int)span; kb.n_cta = (int)n_cta_b; kb.W_dec = (int)wd; kb.be_lanes = BACK_T;
+		kb.n_extra = 0; kb.n_own = 1; kb.Sf = (int)span; kb.n_cta = (int)n_cta_b; kb.W_dec = (int)wd; kb.be_lanes = back_t;
 		kb.ticket = h->d_sync + 2;
-		const size_t smem_b = (size_t)(BACK_T / 32) * 32 * WIN_ROW_WORDS * sizeof(uint32_t);
-		RXB_CUDA(cudaFuncSetAttribute(fm_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-		int per_b = 1;
-		RXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, fm_back_kernel, BACK_T, smem_b));
-		if (per_b < 1) { per_b = 1; }
 		size_t blocks_b = (size_t)h->n_sm * per_b;
 		if (blocks_b > total_back) { blocks_b = total_back; }
-		fm_back_kernel<<<(unsigned)blocks_b, BACK_T, smem_b, h->stream>>>(dv, kb);
+		kern_back<<<(unsigned)blocks_b, back_t, smem_b, h->stream>>>(dv, kb);
 		RXB_CUDA(cudaGetLastError());
 		RXB_CUDA(cudaEventRecord(h->ev1, h->stream));
 		launches++;

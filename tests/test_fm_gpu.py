@@ -210,16 +210,20 @@ def test_split_kernel_with_segment_front_end(name, seg, port, monkeypatch):
     d.close()
 
 
+@pytest.mark.parametrize("shape", [(64, 32), (128, 32), (128, 128), (256, 64)])
 @pytest.mark.parametrize("piece", [0, 64, 300])
 @pytest.mark.parametrize("name", ["cfg2A", "zeros_deemph", "wbfm_deemph_quiet"])
-def test_stream_path_front_kernel_then_back_kernel(name, piece, port, monkeypatch):
+def test_stream_path_front_kernel_then_back_kernel(name, piece, shape, port, monkeypatch):
     """The undecimated wbfm shape on long calls runs two kernels: the front end of the whole call (PCM to global memory),
     then fm_back_kernel with pieces as long as the call allows.  RXB200_FM_STREAM_MIN=0 selects the path for a test-sized
-    call; RXB200_FM_STREAM_PIECE sets the piece length (several items per channel, look-back between them)."""
+    call; RXB200_FM_STREAM_PIECE sets the piece length (several items per channel, look-back between them);
+    RXB200_FM_STREAM_WIN / _T pick the back kernel's window size and lanes per item."""
     names = [c.name for c in fm_cases()]
     if name not in names:
         pytest.skip("no such case")
     monkeypatch.setenv("RXB200_FM_STREAM_MIN", "0")
+    monkeypatch.setenv("RXB200_FM_STREAM_WIN", str(shape[0]))
+    monkeypatch.setenv("RXB200_FM_STREAM_T", str(shape[1]))
     if piece:
         monkeypatch.setenv("RXB200_FM_STREAM_PIECE", str(piece))
     case = next(c for c in fm_cases() if c.name == name)

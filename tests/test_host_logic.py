@@ -68,3 +68,20 @@ def test_wbfm_preset_keeps_a_later_squelch_level():
     from rx_tools_b200 import fm
     assert fm.derive_params(wbfm=1, squelch_level=50).params.squelch_level == 50
     assert fm.derive_params(wbfm=1).params.squelch_level == 0
+
+
+def test_deemph_fp32_identity():
+    """The CUDA back end runs deemph_filter (src/rtl_fm.c:667-682) for odd a as  U' = fma(X - U, fl(1/a), U)  in FP32
+    with U = 2^23 + 32768 + avg (csrc/fm_kernels.cu, DeemphOp<false, true>).  That is exact iff rounding d * fl(1/a) to
+    the nearest integer equals the reference's trunc((d +- a/2) / a) for every difference d of two int16 values: checked
+    here for every d and a spread of odd a (the kernels' own parity tests cover a = 23 and a = 181 on the GPU)."""
+    d = np.arange(-65535, 65536, dtype=np.int64)
+    for a in list(range(1, 400, 2)) + [1023, 1801, 4095, 18001, 32767]:
+        inv = np.float64(np.float32(1.0) / np.float32(a))
+        h = a // 2
+        num = np.where(d > 0, d + h, d - h)
+        ref = np.sign(num) * (np.abs(num) // a)            # C's truncating division
+        y = d.astype(np.float64) * inv                     # exact: 17 x 24 significant bits
+        assert np.array_equal(np.rint(y).astype(np.int64), ref), a
+        # no tie in sight: the nearest half-integer is further away than any rounding of the fma could reach
+        assert np.min(np.abs((y - np.floor(y)) - 0.5)) > 65536 * 2.0 ** -24 / a
