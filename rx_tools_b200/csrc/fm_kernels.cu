@@ -379,6 +379,35 @@ __device__ __forceinline__ int fast_atan2_i(int y, int x)
 	return y < 0 ? neg_w(ang) : ang;
 }
 
+// fast_atan2 on operands that are exact in FP32 (|x|, |y| <= 2^16: the undecimated shape, where a sample is an 8-bit-range
+// value and the conjugate product at most 2 * 128^2).  FP32 adds and multiply-adds issue every cycle, the integer
+// adder / shifter pipe every other one (tools/experiments/op_microbench.cu), and the integer form above is mostly
+// adder-pipe work.  Every quantity below is an integer held exactly in a float:
+//   den = |x| + |y|,  n = |x| - |y|,  T = floor(4096 |n| / den)  (estimate from a reciprocal biased low by 2^-20 --
+//   never above the true quotient, at most one below -- then one exact remainder check: fma(-T, den, 4096 |n|)),
+//   x >= 0: 4096 - sgn(n) T        x < 0: 12288 + sgn(n) T        negated for y < 0        0 for x == y == 0
+// which is the reference's truncating integer division on both branches (src/rtl_fm.c:485-506).  Returns the angle as
+// an integer-valued float.
+#ifndef DISC_F32
+#define DISC_F32 1
+#endif
+__device__ __forceinline__ float fast_atan2_f32(float y, float x)
+{
+	const float ax = fabsf(x), ay = fabsf(y);
+	const float den = __fadd_rn(ax, ay);
+	const float n = __fsub_rn(ax, ay);
+	const float an = __fmul_rn(fabsf(n), 4096.0f);
+	float te = __fmul_rn(an, rcp_est(den));
+	te = __fmaf_rn(te, -9.5367431640625e-07f, te);                       // * (1 - 2^-20)
+	float T = __fsub_rn(__fadd_rd(te, 12582912.0f), 12582912.0f);        // floor(te): round-down add of 1.5 * 2^23
+	const float rem = __fmaf_rn(-T, den, an);                            // exact
+	if (rem >= den) { T = __fadd_rn(T, 1.0f); }
+	const float Ts = __int_as_float(__float_as_int(T) ^ (__float_as_int(n) & (int)0x80000000));      // sgn(n) T  (n is never -0)
+	const float ang = (x >= 0.0f) ? __fsub_rn(4096.0f, Ts) : __fadd_rn(12288.0f, Ts);
+	const float r = (y < 0.0f) ? -ang : ang;
+	return (den == 0.0f) ? 0.0f : r;
+}
+
 // polar_disc_lut (src/rtl_fm.c:528-564)
 __device__ __forceinline__ int disc_lut(const int *__restrict__ lut, int cr, int cj)
 {
@@ -634,6 +663,33 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 			// no decimation (-s at or above 1 Msps): every input sample is a PCM sample and a block is 8 consecutive entries of
 			// the global PCM array, 16-byte aligned (segments and halos are multiples of 8) -- one vector store per block
 			// instead of eight 2-byte stores to 32 different lines per warp.  Same arithmetic as post_decim's FM branch.
+#if DISC_F32
+			// the discriminator in FP32 (exact: see fast_atan2_f32); the angle leaves through the low 16 bits of
+			// angle + 1.5 * 2^23, two samples per byte permute
+			uint32_t ab[8];
+			float br = __int2float_rn(s.pre_i), bj = __int2float_rn(s.pre_q);
+			int di = s.pre_i, dq = s.pre_q;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				scale_rot(v[j], j, rot, di, dq);
+				const float fi = __int2float_rn(di), fq = __int2float_rn(dq);
+				const float cr = __fmaf_rn(fi, br, __fmul_rn(fq, bj));
+				const float cj = __fmaf_rn(fq, br, -__fmul_rn(fi, bj));
+				float ang = fast_atan2_f32(cj, cr);
+				// F8: the chunk's first sample (chunks start on block boundaries) goes through the libm discriminator
+				if (j == 0 && e.first_in_chunk) { ang = __int2float_rn(disc_std(__float2int_rn(cr), __float2int_rn(cj))); }
+				ab[j] = (uint32_t)__float_as_int(__fadd_rn(ang, 12582912.0f));
+				br = fi; bj = fq;
+			}
+			s.pre_i = di; s.pre_q = dq;
+			e.first_in_chunk = 0;
+			if (STORE) {
+				uint4 w;
+				w.x = __byte_perm(ab[0], ab[1], 0x5410); w.y = __byte_perm(ab[2], ab[3], 0x5410);
+				w.z = __byte_perm(ab[4], ab[5], 0x5410); w.w = __byte_perm(ab[6], ab[7], 0x5410);
+				*reinterpret_cast<uint4 *>(e.out + e.m_lo + e.rel) = w;
+			}
+#else
 			int a[8];
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
@@ -652,6 +708,7 @@ __device__ __forceinline__ void front_block(const FmDev &c, const FmCall &k, Fro
 				w.x = pack2(a[0], a[1]); w.y = pack2(a[2], a[3]); w.z = pack2(a[4], a[5]); w.w = pack2(a[6], a[7]);
 				*reinterpret_cast<uint4 *>(e.out + e.m_lo + e.rel) = w;
 			}
+#endif
 			e.rel += 8;
 			return;
 		}
@@ -738,6 +795,9 @@ struct DeemphOp {
 	__device__ __forceinline__ DeemphOp(const FmDev &c) : bias(c.a_half + c.a_K * c.a), K(c.a_K), magic(c.a_magic) {}
 	__device__ __forceinline__ State enter(int avg) const { return avg; }
 	__device__ __forceinline__ int value(State s) const { return s; }
+	typedef int Raw;                            // a sample as fetched (loops that fetch ahead carry these), conv() makes it a Sample
+	__device__ __forceinline__ Raw fetch(const int16_t *p) const { return (int)*p; }
+	__device__ __forceinline__ Sample conv(Raw r) const { return r; }
 	__device__ __forceinline__ Sample load(const int16_t *p) const { return (int)*p; }
 	__device__ __forceinline__ State step(State s, Sample x) const { return deemph_fast<EVEN>(s, x, x + bias, magic, K); }
 };
@@ -749,10 +809,16 @@ struct DeemphOp<false, true> {
 	__device__ __forceinline__ DeemphOp(const FmDev &c) : inv_a(1.0f / (float)c.a) {}
 	__device__ __forceinline__ State enter(int avg) const { return __int_as_float(DF_BIAS + avg); }
 	__device__ __forceinline__ int value(State s) const { return __float_as_int(s) - DF_BIAS; }
-	__device__ __forceinline__ Sample load(const int16_t *p) const
+	typedef unsigned Raw;
+	__device__ __forceinline__ Raw fetch(const int16_t *p) const
 	{
-		return __int_as_float((int)(((unsigned)*reinterpret_cast<const uint16_t *>(p) ^ 0x8000u) | 0x4B000000u));
+		unsigned v = *reinterpret_cast<const uint16_t *>(p);
+		asm("" : "+r"(v));      // 32 bits from here on (left alone the compiler carries 16-bit values across loop edges two to a
+		                        // register and pays a mask and a permute per sample to get them back)
+		return v;
 	}
+	__device__ __forceinline__ Sample conv(Raw v) const { return __int_as_float((int)(v ^ 0x4B008000u)); }   // 16 bits: the xor sets the exponent too
+	__device__ __forceinline__ Sample load(const int16_t *p) const { return conv(fetch(p)); }
 	__device__ __forceinline__ State step(State s, Sample x) const { return __fmaf_rn(__fsub_rn(x, s), inv_a, s); }
 };
 template <bool EVEN>
@@ -774,14 +840,46 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 			const typename Deemph<EVEN>::Sample x = dm.load(pcm_s + pcm_phys<PAD>(m));
 			l = dm.step(l, x); h = dm.step(h, x);
 		}
-#pragma unroll 2
-		for (; m + 4 <= m_end; m += 4) {
+		// PAD == 0 (consecutive samples are consecutive entries): eight steps per trip, the NEXT eight samples fetched before
+		// them -- a shared-memory load under the window fills' traffic takes longer than four steps of the two chains, and
+		// the compiler does not move loads across the loop edge by itself.  The last trip re-reads its own samples.
+		if constexpr (PAD == 0) {
+			if (m + 8 <= m_end) {
+				typedef typename Deemph<EVEN>::Raw Raw;
+				const int16_t *q = pcm_s + m;
+				Raw r0 = dm.fetch(q), r1 = dm.fetch(q + 1), r2 = dm.fetch(q + 2), r3 = dm.fetch(q + 3);
+				Raw r4 = dm.fetch(q + 4), r5 = dm.fetch(q + 5), r6 = dm.fetch(q + 6), r7 = dm.fetch(q + 7);
+				for (; m + 8 <= m_end; m += 8) {
+					const int16_t *qn = q + (m + 16 <= m_end ? 8 : 0);
+					const Raw n0 = dm.fetch(qn), n1 = dm.fetch(qn + 1), n2 = dm.fetch(qn + 2), n3 = dm.fetch(qn + 3);
+					const Raw n4 = dm.fetch(qn + 4), n5 = dm.fetch(qn + 5), n6 = dm.fetch(qn + 6), n7 = dm.fetch(qn + 7);
+					typename Deemph<EVEN>::Sample x;
+					x = dm.conv(r0); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r1); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r2); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r3); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r4); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r5); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r6); l = dm.step(l, x); h = dm.step(h, x);
+					x = dm.conv(r7); l = dm.step(l, x); h = dm.step(h, x);
+					r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7;
+					q = qn;
+				}
+			}
+		}
+		if (m + 4 <= m_end) {
 			const int16_t *q = pcm_s + pcm_phys<PAD>(m);
-			const typename Deemph<EVEN>::Sample x0 = dm.load(q), x1 = dm.load(q + 1), x2 = dm.load(q + 2), x3 = dm.load(q + 3);
-			l = dm.step(l, x0); h = dm.step(h, x0);
-			l = dm.step(l, x1); h = dm.step(h, x1);
-			l = dm.step(l, x2); h = dm.step(h, x2);
-			l = dm.step(l, x3); h = dm.step(h, x3);
+			typename Deemph<EVEN>::Sample x0 = dm.load(q), x1 = dm.load(q + 1), x2 = dm.load(q + 2), x3 = dm.load(q + 3);
+#pragma unroll 2
+			for (; m + 4 <= m_end; m += 4) {
+				const int16_t *qn = pcm_s + pcm_phys<PAD>(m + 8 <= m_end ? m + 4 : m);
+				const typename Deemph<EVEN>::Sample y0 = dm.load(qn), y1 = dm.load(qn + 1), y2 = dm.load(qn + 2), y3 = dm.load(qn + 3);
+				l = dm.step(l, x0); h = dm.step(h, x0);
+				l = dm.step(l, x1); h = dm.step(h, x1);
+				l = dm.step(l, x2); h = dm.step(h, x2);
+				l = dm.step(l, x3); h = dm.step(h, x3);
+				x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+			}
 		}
 		for (; m < m_end; m++) {
 			const typename Deemph<EVEN>::Sample x = dm.load(pcm_s + pcm_phys<PAD>(m));
@@ -892,13 +990,19 @@ __device__ __forceinline__ void back_outputs_lean(const FmDev &c, const int16_t 
 			// any ratio (the undecimated wbfm shape has 50 samples per output): quads, then the rest
 			const int len = lf + (extra ? 1 : 0);
 			int j = 0;
-			for (; j + 4 <= len; j += 4) {
-				const Smp x0 = de.load(p), x1 = de.load(p + 1), x2 = de.load(p + 2), x3 = de.load(p + 3);
-				a = de.step(a, x0); acc += de.value(a);
-				a = de.step(a, x1); acc += de.value(a);
-				a = de.step(a, x2); acc += de.value(a);
-				a = de.step(a, x3); acc += de.value(a);
-				p += 4;
+			if (len >= 4) {
+				Smp x0 = de.load(p), x1 = de.load(p + 1), x2 = de.load(p + 2), x3 = de.load(p + 3);
+#pragma unroll 2
+				for (; j + 4 <= len; j += 4) {
+					const int16_t *pn = p + (j + 8 <= len ? 4 : 0);
+					const Smp y0 = de.load(pn), y1 = de.load(pn + 1), y2 = de.load(pn + 2), y3 = de.load(pn + 3);
+					a = de.step(a, x0); acc += de.value(a);
+					a = de.step(a, x1); acc += de.value(a);
+					a = de.step(a, x2); acc += de.value(a);
+					a = de.step(a, x3); acc += de.value(a);
+					x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+					p += 4;
+				}
 			}
 			for (; j < len; j++) {
 				const Smp x = de.load(p++);
@@ -974,35 +1078,38 @@ __device__ __forceinline__ void back_outputs(const FmDev &c, const int16_t *pcm_
 // the phase alone.  Odd row stride: lanes reading the same offset of their rows hit 32 different banks.
 template <int WS>
 struct LaneWin {
-	static constexpr int ROW = WS / 2 + 1;      // words per row
+	static constexpr int ROW = WS / 2 + 2;      // words per row: even (8-byte copies), lanes 16 apart share a bank
 	static constexpr int BUF = 32 * ROW;        // words per buffer (one row per lane)
 	const int16_t *g;         // the channel's PCM in global memory
 	uint32_t *rows;           // this warp's two buffers
 	int lane;
 };
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
 {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// all 32 lanes: lane l's row of buffer `buf` <- g[base_l .. base_l + WS), base_l even; one commit group per call
+// all 32 lanes: lane l's row of buffer `buf` <- g[base_l .. base_l + WS), base_l a multiple of 4 samples (8-byte copies:
+// the copy instruction, not its bytes, is what the load/store unit charges for -- session W: 64 four-byte copies per
+// window kept the unit busy most of the time); one commit group per call
+#define WIN_ALIGN 3
 template <int WS>
 __device__ __forceinline__ void win_issue(const LaneWin<WS> &w, int buf, int base)
 {
-	constexpr int NV = WS / 64;
-	const uint32_t dst0 = smem_u32(w.rows + buf * LaneWin<WS>::BUF + w.lane);
+	constexpr int NV = WS / 128;
+	const uint32_t dst0 = smem_u32(w.rows + buf * LaneWin<WS>::BUF + 2 * w.lane);
 	// fully unrolled: the destination of every copy is dst0 plus a compile-time offset, a row costs one shuffle, one
 	// address and its copies
-	const char *gl = reinterpret_cast<const char *>(w.g) + 4 * w.lane;      // this lane's word of every row
+	const char *gl = reinterpret_cast<const char *>(w.g) + 8 * w.lane;      // this lane's eight bytes of every row
 #pragma unroll
 	for (int l = 0; l < 32; l++) {
 		const unsigned b = (unsigned)__shfl_sync(0xffffffffu, base, l);       // bases are never negative: one 32 x 32 -> 64 multiply-add
-		const uint32_t *src = reinterpret_cast<const uint32_t *>(gl + 2ull * b);
+		const char *src = gl + 2ull * b;
 		const uint32_t dst = dst0 + (uint32_t)(l * LaneWin<WS>::ROW * 4);
 #pragma unroll
-		for (int i = 0; i < NV; i++) { cp_async4(dst + 128u * i, src + 32 * i); }
+		for (int i = 0; i < NV; i++) { cp_async8(dst + 256u * i, src + 256 * i); }
 	}
 	cp_async_commit();
 }
@@ -1012,20 +1119,20 @@ template <bool EVEN, int WS>
 __device__ __forceinline__ void win_replay(const FmDev &c, const LaneWin<WS> &w, int m, int m_end, int &lo, int &hi)
 {
 	if (!__any_sync(0xffffffffu, m < m_end)) { return; }
-	int base = m & ~1, buf = 0;
+	int base = m & ~WIN_ALIGN, buf = 0;
 	__syncwarp();
 	win_issue(w, 0, base);
 	for (;;) {
 		const int e = m_end < base + WS ? m_end : base + WS;
 		const int m_next = m < e ? e : m;
 		const bool more = __any_sync(0xffffffffu, m_next < m_end);
-		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+		if (more) { win_issue(w, buf ^ 1, m_next & ~WIN_ALIGN); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
 		const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW);
 		if (m < e) { back_replay<EVEN, 0>(c, row - base, m, e, lo, hi); }
 		__syncwarp();                          // every lane is through with this buffer before the next fill but one lands in it
 		if (!more) { break; }
-		m = m_next; base = m_next & ~1; buf ^= 1;
+		m = m_next; base = m_next & ~WIN_ALIGN; buf ^= 1;
 	}
 }
 // back_probe over PCM [m, m_end) through windows (an open bracket's piece); returns the lane's `moved` word
@@ -1034,20 +1141,20 @@ __device__ __forceinline__ int win_probe(const FmDev &c, const LaneWin<WS> &w, i
 {
 	int moved = 0;
 	if (!__any_sync(0xffffffffu, m < m_end)) { return moved; }
-	int base = m & ~1, buf = 0;
+	int base = m & ~WIN_ALIGN, buf = 0;
 	__syncwarp();
 	win_issue(w, 0, base);
 	for (;;) {
 		const int e = m_end < base + WS ? m_end : base + WS;
 		const int m_next = m < e ? e : m;
 		const bool more = __any_sync(0xffffffffu, m_next < m_end);
-		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+		if (more) { win_issue(w, buf ^ 1, m_next & ~WIN_ALIGN); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
 		const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW);
 		if (m < e) { moved |= back_probe<EVEN, 0>(c, row - base, m, e, lo, hi); }
 		__syncwarp();
 		if (!more) { break; }
-		m = m_next; base = m_next & ~1; buf ^= 1;
+		m = m_next; base = m_next & ~WIN_ALIGN; buf ^= 1;
 	}
 	return moved;
 }
@@ -1075,49 +1182,60 @@ __device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin<WS> &w
 		if (extra) { ph += slow; }
 		phase = ph - fast; g_left = lf + (extra ? 1 : 0);
 	}
-	int base = mm & ~1, buf = 0;
+	typedef typename Deemph<EVEN>::Raw Raw;
+	auto emit = [&]() {                        // the group is complete: its output, then the next group's length
+		int q = __mulhi(acc, dm);
+		if (dadd) { q += acc; }
+		q >>= dsh;
+		q += (int)((unsigned)q >> 31);
+		*op++ = (int16_t)q;
+		acc = 0;
+		int ph = phase + lf * slow;
+		const bool extra = ph < fast;
+		if (extra) { ph += slow; }
+		phase = ph - fast; g_left = lf + (extra ? 1 : 0);
+	};
+	int base = mm & ~WIN_ALIGN, buf = 0;
 	__syncwarp();
 	win_issue(w, 0, base);
 	for (;;) {
 		const int e = m_stop < base + WS ? m_stop : base + WS;
 		const int m_next = mm < e ? e : mm;
 		const bool more = __any_sync(0xffffffffu, m_next < m_stop);
-		if (more) { win_issue(w, buf ^ 1, m_next & ~1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+		if (more) { win_issue(w, buf ^ 1, m_next & ~WIN_ALIGN); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
 		const int16_t *p = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW) + (mm - base);
-		while (mm < e) {
-			int run = e - mm;
-			if (run > g_left) { run = g_left; }
-			int j = 0;
-			for (; j + 4 <= run; j += 4) {
-				const Smp x0 = de.load(p), x1 = de.load(p + 1), x2 = de.load(p + 2), x3 = de.load(p + 3);
-				a = de.step(a, x0); acc += de.value(a);
-				a = de.step(a, x1); acc += de.value(a);
-				a = de.step(a, x2); acc += de.value(a);
-				a = de.step(a, x3); acc += de.value(a);
-				p += 4;
+		// The window's samples as a stream of quads fetched TWO quads ahead (a shared-memory load under the fills' traffic
+		// takes longer than four steps); a resampler group ends wherever it ends: a quad that holds a group boundary
+		// takes the per-sample path.  The read-ahead runs at most eleven samples past the lane's last one: inside the
+		// row's slack, the next row, or the slack behind the last buffer (fm_launch adds it) -- never used.
+		int avail = mm < e ? e - mm : 0;
+		Raw q0 = de.fetch(p), q1 = de.fetch(p + 1), q2 = de.fetch(p + 2), q3 = de.fetch(p + 3);
+		Raw q4 = de.fetch(p + 4), q5 = de.fetch(p + 5), q6 = de.fetch(p + 6), q7 = de.fetch(p + 7);
+		while (avail >= 4) {
+			const Raw n0 = de.fetch(p + 8), n1 = de.fetch(p + 9), n2 = de.fetch(p + 10), n3 = de.fetch(p + 11);
+			if (g_left > 4) {
+				a = de.step(a, de.conv(q0)); acc += de.value(a);
+				a = de.step(a, de.conv(q1)); acc += de.value(a);
+				a = de.step(a, de.conv(q2)); acc += de.value(a);
+				a = de.step(a, de.conv(q3)); acc += de.value(a);
+				g_left -= 4;
+			} else {
+				a = de.step(a, de.conv(q0)); acc += de.value(a); if (--g_left == 0) { emit(); }
+				a = de.step(a, de.conv(q1)); acc += de.value(a); if (--g_left == 0) { emit(); }
+				a = de.step(a, de.conv(q2)); acc += de.value(a); if (--g_left == 0) { emit(); }
+				a = de.step(a, de.conv(q3)); acc += de.value(a); if (--g_left == 0) { emit(); }
 			}
-			for (; j < run; j++) {
-				const Smp x = de.load(p++);
-				a = de.step(a, x); acc += de.value(a);
-			}
-			mm += run; g_left -= run;
-			if (g_left == 0) {
-				int q = __mulhi(acc, dm);
-				if (dadd) { q += acc; }
-				q >>= dsh;
-				q += (int)((unsigned)q >> 31);
-				*op++ = (int16_t)q;
-				acc = 0;
-				int ph = phase + lf * slow;
-				const bool extra = ph < fast;
-				if (extra) { ph += slow; }
-				phase = ph - fast; g_left = lf + (extra ? 1 : 0);
-			}
+			q0 = q4; q1 = q5; q2 = q6; q3 = q7; q4 = n0; q5 = n1; q6 = n2; q7 = n3;
+			p += 4; avail -= 4;
 		}
+		if (avail > 0) { a = de.step(a, de.conv(q0)); acc += de.value(a); if (--g_left == 0) { emit(); } }
+		if (avail > 1) { a = de.step(a, de.conv(q1)); acc += de.value(a); if (--g_left == 0) { emit(); } }
+		if (avail > 2) { a = de.step(a, de.conv(q2)); acc += de.value(a); if (--g_left == 0) { emit(); } }
+		if (mm < e) { mm = e; }
 		__syncwarp();
 		if (!more) { break; }
-		base = m_next & ~1; buf ^= 1;
+		base = m_next & ~WIN_ALIGN; buf ^= 1;
 	}
 	m = mm; avg = de.value(a);
 }
@@ -1541,7 +1659,7 @@ __global__ void __launch_bounds__(T, (FM_MAX_THREADS / T) * (SPEC == 2 ? (P <= 3
 template <int WS, int T>
 __global__ void __launch_bounds__(T) fm_back_kernel(const FmDev c, const FmCall k)
 {
-	extern __shared__ __align__(16) uint32_t win_s[];      // [T / 32][2][32][WS / 2 + 1]
+	extern __shared__ __align__(16) uint32_t win_s[];      // [T / 32][2][32][WS / 2 + 2]
 	__shared__ int s_work;
 	__shared__ int s_avg[T], s_mrun[T], s_start[T];
 	__shared__ unsigned char s_ok[T];
@@ -1562,7 +1680,6 @@ typedef void (*fm_kernel_fn)(const FmDev, const FmCall);
 static fm_kernel_fn pick_back_kernel(int ws, int t)
 {
 	if (ws == 256) { return t == 32 ? fm_back_kernel<256, 32> : (t == 64 ? fm_back_kernel<256, 64> : fm_back_kernel<256, 128>); }
-	if (ws == 64) { return t == 32 ? fm_back_kernel<64, 32> : (t == 64 ? fm_back_kernel<64, 64> : fm_back_kernel<64, 128>); }
 	return t == 32 ? fm_back_kernel<128, 32> : (t == 64 ? fm_back_kernel<128, 64> : fm_back_kernel<128, 128>);
 }
 
@@ -1986,7 +2103,7 @@ extern "C" int rxb200_fm_create(const rxb200_fm_params *params, int device, int 
 		h->stream_piece = getenv("RXB200_FM_STREAM_PIECE") ? atoi(getenv("RXB200_FM_STREAM_PIECE")) : 0;
 		{
 			const int ws = getenv("RXB200_FM_STREAM_WIN") ? atoi(getenv("RXB200_FM_STREAM_WIN")) : 0;
-			h->stream_win = (ws == 64 || ws == 128 || ws == 256) ? ws : 128;
+			h->stream_win = (ws == 128 || ws == 256) ? ws : 128;
 			const int t = getenv("RXB200_FM_STREAM_T") ? atoi(getenv("RXB200_FM_STREAM_T")) : 0;
 			h->stream_t = (t == 32 || t == 64 || t == 128) ? t : 32;
 			const int wa = getenv("RXB200_FM_STREAM_WARM_A") ? atoi(getenv("RXB200_FM_STREAM_WARM_A")) : 0;
@@ -2427,7 +2544,7 @@ static int fm_launch(rxb200_fm *h, const int16_t *d_in, size_t n_int16, size_t c
 	long long piece = 0, span = 0, n_cta_b = 0, pstride = 0;
 	const int back_t = h->stream_t, back_ws = h->stream_win;
 	const fm_kernel_fn kern_back = pick_back_kernel(back_ws, back_t);
-	const size_t smem_b = (size_t)(back_t / 32) * 2 * 32 * (back_ws / 2 + 1) * sizeof(uint32_t);
+	const size_t smem_b = (size_t)(back_t / 32) * 2 * 32 * (back_ws / 2 + 2) * sizeof(uint32_t) + 64;      // + slack for win_outputs' read-ahead
 	int per_b = 1;
 	if (stream) {
 		RXB_CUDA(cudaFuncSetAttribute(kern_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));

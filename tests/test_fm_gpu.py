@@ -210,7 +210,7 @@ def test_split_kernel_with_segment_front_end(name, seg, port, monkeypatch):
     d.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 32), (128, 32), (128, 128), (256, 64)])
+@pytest.mark.parametrize("shape", [(128, 32), (128, 128), (256, 32), (256, 64)])
 @pytest.mark.parametrize("piece", [0, 64, 300])
 @pytest.mark.parametrize("name", ["cfg2A", "zeros_deemph", "wbfm_deemph_quiet"])
 def test_stream_path_front_kernel_then_back_kernel(name, piece, shape, port, monkeypatch):

@@ -85,3 +85,56 @@ def test_deemph_fp32_identity():
         assert np.array_equal(np.rint(y).astype(np.int64), ref), a
         # no tie in sight: the nearest half-integer is further away than any rounding of the fma could reach
         assert np.min(np.abs((y - np.floor(y)) - 0.5)) > 65536 * 2.0 ** -24 / a
+
+
+def _fast_atan2_ref(y, x):
+    """fast_atan2 (src/rtl_fm.c:485-506) on int64 arrays, C's truncating division."""
+    ya = np.abs(y)
+    num = np.where(x >= 0, 4096 * (x - ya), 4096 * (x + ya))
+    den = np.where(x >= 0, x + ya, ya - x)
+    den1 = np.where(den == 0, 1, den)
+    q = np.sign(num) * (np.abs(num) // den1)
+    ang = np.where(x >= 0, 4096 - q, 12288 - q)
+    ang = np.where(y < 0, -ang, ang)
+    return np.where((x == 0) & (y == 0), 0, ang)
+
+
+def _fast_atan2_f32(y, x, ulp_shift):
+    """The FP32 restatement the CUDA front end uses where the operands are exact in a float (fast_atan2_f32,
+    csrc/fm_kernels.cu), step for step in numpy float32; `ulp_shift` moves the reciprocal estimate by that many ulps
+    (the hardware's rcp.approx is within one ulp of the rounded reciprocal)."""
+    f = np.float32
+    x = x.astype(f); y = y.astype(f)
+    ax, ay = np.abs(x), np.abs(y)
+    den = ax + ay
+    n = ax - ay
+    an = np.abs(n) * f(4096.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rc = (f(1.0) / den).astype(f)
+        rc = np.where(np.isfinite(rc), (rc.view(np.int32) + ulp_shift).view(f), rc)
+        te = (an * rc).astype(f)
+        te = (te.astype(np.float64) * (1.0 - 2.0 ** -20)).astype(f)          # fma(te, -2^-20, te)
+        T = np.floor(te).astype(f)                                            # round-down add of 1.5 * 2^23, minus it
+        rem = an.astype(np.float64) - T.astype(np.float64) * den.astype(np.float64)   # fma(-T, den, an): exact
+        T = np.where(rem >= den, T + f(1.0), T)
+        Ts = np.where(n < 0, -T, T)
+        ang = np.where(x >= 0, f(4096.0) - Ts, f(12288.0) + Ts)
+        r = np.where(y < 0, -ang, ang)
+    return np.where(den == 0, 0, r).astype(np.int64)
+
+
+def test_fast_atan2_fp32_form():
+    rng = np.random.default_rng(7)
+    # every pair of small operands, then random pairs over the whole range the undecimated shape can produce (|.| <= 2^15),
+    # the quadrant edges and the ratios whose quotient is an exact integer
+    g = np.arange(-260, 261, dtype=np.int64)
+    xs, ys = [np.repeat(g, g.size)], [np.tile(g, g.size)]
+    xs.append(rng.integers(-32768, 32769, 4_000_000)); ys.append(rng.integers(-32768, 32769, 4_000_000))
+    k = rng.integers(1, 4097, 500_000); d = rng.integers(1, 16, 500_000) * 4096          # n / den = k / 4096 exactly
+    xs.append((d + k * (d // 4096)) // 2); ys.append((d - k * (d // 4096)) // 2)
+    edge = np.array([-32768, -32767, -1, 0, 1, 32767, 32768], dtype=np.int64)
+    xs.append(np.repeat(edge, edge.size)); ys.append(np.tile(edge, edge.size))
+    x = np.concatenate(xs); y = np.concatenate(ys)
+    want = _fast_atan2_ref(y, x)
+    for shift in (-1, 0, 1):
+        assert np.array_equal(_fast_atan2_f32(y, x, shift), want), shift
