@@ -799,6 +799,12 @@ struct DeemphOp {
 	__device__ __forceinline__ Raw fetch(const int16_t *p) const { return (int)*p; }
 	__device__ __forceinline__ Sample conv(Raw r) const { return r; }
 	__device__ __forceinline__ Sample load(const int16_t *p) const { return (int)*p; }
+	// four samples from an 8-byte aligned address: one load
+	__device__ __forceinline__ void load4(const int16_t *p, Sample &x0, Sample &x1, Sample &x2, Sample &x3) const
+	{
+		const uint2 w = *reinterpret_cast<const uint2 *>(p);
+		x0 = lo16(w.x); x1 = hi16(w.x); x2 = lo16(w.y); x3 = hi16(w.y);
+	}
 	__device__ __forceinline__ State step(State s, Sample x) const { return deemph_fast<EVEN>(s, x, x + bias, magic, K); }
 };
 template <>
@@ -818,7 +824,22 @@ struct DeemphOp<false, true> {
 		return v;
 	}
 	__device__ __forceinline__ Sample conv(Raw v) const { return __int_as_float((int)(v ^ 0x4B008000u)); }   // 16 bits: the xor sets the exponent too
-	__device__ __forceinline__ Sample load(const int16_t *p) const { return conv(fetch(p)); }
+	__device__ __forceinline__ Sample load(const int16_t *p) const
+	{
+		float x = __int_as_float((int)((unsigned)*reinterpret_cast<const uint16_t *>(p) ^ 0x4B008000u));
+		asm("" : "+f"(x));      // a float from here on (same reason)
+		return x;
+	}
+	__device__ __forceinline__ void load4(const int16_t *p, Sample &x0, Sample &x1, Sample &x2, Sample &x3) const
+	{
+		const uint2 w = *reinterpret_cast<const uint2 *>(p);
+		unsigned magic = 0x4B008000u, l0, l1;
+		asm("" : "+r"(magic));                 // in a register: (w & 0xffff) ^ magic is then ONE three-input logic instruction
+		asm("lop3.b32 %0, %1, 0xffff, %2, 0x6a;" : "=r"(l0) : "r"(w.x), "r"(magic));
+		asm("lop3.b32 %0, %1, 0xffff, %2, 0x6a;" : "=r"(l1) : "r"(w.y), "r"(magic));
+		x0 = __int_as_float((int)l0); x1 = __int_as_float((int)((w.x >> 16) ^ magic));
+		x2 = __int_as_float((int)l1); x3 = __int_as_float((int)((w.y >> 16) ^ magic));
+	}
 	__device__ __forceinline__ State step(State s, Sample x) const { return __fmaf_rn(__fsub_rn(x, s), inv_a, s); }
 };
 template <bool EVEN>
@@ -828,7 +849,8 @@ struct Deemph : DeemphOp<EVEN, (!EVEN && DEEMPH_F32 != 0)> {
 
 // deemph_filter over PCM [m, m_end) of the shared buffer from BOTH bracket ends (replay before a
 // piece).  The two trajectories are independent, the next sample is fetched one step ahead.
-template <bool EVEN, int PAD>
+// A8: pcm_s + m is 8-byte aligned whenever m is a multiple of 4 (the back kernel's windows): a quad is ONE 8-byte load.
+template <bool EVEN, int PAD, bool A8 = false>
 __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s, int m, int m_end, int &lo, int &hi)
 {
 	if (m >= m_end) { return; }
@@ -840,45 +862,26 @@ __device__ __forceinline__ void back_replay(const FmDev &c, const int16_t *pcm_s
 			const typename Deemph<EVEN>::Sample x = dm.load(pcm_s + pcm_phys<PAD>(m));
 			l = dm.step(l, x); h = dm.step(h, x);
 		}
-		// PAD == 0 (consecutive samples are consecutive entries): eight steps per trip, the NEXT eight samples fetched before
-		// them -- a shared-memory load under the window fills' traffic takes longer than four steps of the two chains, and
-		// the compiler does not move loads across the loop edge by itself.  The last trip re-reads its own samples.
-		if constexpr (PAD == 0) {
-			if (m + 8 <= m_end) {
-				typedef typename Deemph<EVEN>::Raw Raw;
-				const int16_t *q = pcm_s + m;
-				Raw r0 = dm.fetch(q), r1 = dm.fetch(q + 1), r2 = dm.fetch(q + 2), r3 = dm.fetch(q + 3);
-				Raw r4 = dm.fetch(q + 4), r5 = dm.fetch(q + 5), r6 = dm.fetch(q + 6), r7 = dm.fetch(q + 7);
-				for (; m + 8 <= m_end; m += 8) {
-					const int16_t *qn = q + (m + 16 <= m_end ? 8 : 0);
-					const Raw n0 = dm.fetch(qn), n1 = dm.fetch(qn + 1), n2 = dm.fetch(qn + 2), n3 = dm.fetch(qn + 3);
-					const Raw n4 = dm.fetch(qn + 4), n5 = dm.fetch(qn + 5), n6 = dm.fetch(qn + 6), n7 = dm.fetch(qn + 7);
-					typename Deemph<EVEN>::Sample x;
-					x = dm.conv(r0); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r1); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r2); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r3); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r4); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r5); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r6); l = dm.step(l, x); h = dm.step(h, x);
-					x = dm.conv(r7); l = dm.step(l, x); h = dm.step(h, x);
-					r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7;
-					q = qn;
-				}
-			}
-		}
+		// the next quad's samples are fetched before this quad's steps (the compiler does not move the loads across the loop
+		// edge by itself); the last quad re-reads itself.  (Deeper read-ahead -- eight steps per trip with the next eight
+		// samples in flight -- measured slower, session AA: the register shuffling costs more than the latency it hides.)
 		if (m + 4 <= m_end) {
 			const int16_t *q = pcm_s + pcm_phys<PAD>(m);
-			typename Deemph<EVEN>::Sample x0 = dm.load(q), x1 = dm.load(q + 1), x2 = dm.load(q + 2), x3 = dm.load(q + 3);
+			typename Deemph<EVEN>::Sample x0, x1, x2, x3;
+			if constexpr (A8) { dm.load4(q, x0, x1, x2, x3); } else { x0 = dm.load(q); x1 = dm.load(q + 1); x2 = dm.load(q + 2); x3 = dm.load(q + 3); }
 #pragma unroll 2
 			for (; m + 4 <= m_end; m += 4) {
-				const int16_t *qn = pcm_s + pcm_phys<PAD>(m + 8 <= m_end ? m + 4 : m);
-				const typename Deemph<EVEN>::Sample y0 = dm.load(qn), y1 = dm.load(qn + 1), y2 = dm.load(qn + 2), y3 = dm.load(qn + 3);
+				// (windows: the read-ahead of the last quad lands in the row's four samples of slack -- no clamp, so the
+				// load's address does not hang on a compare and a select and can issue at the top of the trip)
+				const int16_t *qn = A8 ? q + 4 : pcm_s + pcm_phys<PAD>(m + 8 <= m_end ? m + 4 : m);
+				typename Deemph<EVEN>::Sample y0, y1, y2, y3;
+				if constexpr (A8) { dm.load4(qn, y0, y1, y2, y3); } else { y0 = dm.load(qn); y1 = dm.load(qn + 1); y2 = dm.load(qn + 2); y3 = dm.load(qn + 3); }
 				l = dm.step(l, x0); h = dm.step(h, x0);
 				l = dm.step(l, x1); h = dm.step(h, x1);
 				l = dm.step(l, x2); h = dm.step(h, x2);
 				l = dm.step(l, x3); h = dm.step(h, x3);
 				x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+				q = qn;
 			}
 		}
 		for (; m < m_end; m++) {
@@ -1129,7 +1132,7 @@ __device__ __forceinline__ void win_replay(const FmDev &c, const LaneWin<WS> &w,
 		if (more) { win_issue(w, buf ^ 1, m_next & ~WIN_ALIGN); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
 		const int16_t *row = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW);
-		if (m < e) { back_replay<EVEN, 0>(c, row - base, m, e, lo, hi); }
+		if (m < e) { back_replay<EVEN, 0, true>(c, row - base, m, e, lo, hi); }      // rows and bases are 8-byte aligned
 		__syncwarp();                          // every lane is through with this buffer before the next fill but one lands in it
 		if (!more) { break; }
 		m = m_next; base = m_next & ~WIN_ALIGN; buf ^= 1;
@@ -1182,7 +1185,6 @@ __device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin<WS> &w
 		if (extra) { ph += slow; }
 		phase = ph - fast; g_left = lf + (extra ? 1 : 0);
 	}
-	typedef typename Deemph<EVEN>::Raw Raw;
 	auto emit = [&]() {                        // the group is complete: its output, then the next group's length
 		int q = __mulhi(acc, dm);
 		if (dadd) { q += acc; }
@@ -1205,34 +1207,40 @@ __device__ __forceinline__ void win_outputs(const FmDev &c, const LaneWin<WS> &w
 		if (more) { win_issue(w, buf ^ 1, m_next & ~WIN_ALIGN); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
 		__syncwarp();
 		const int16_t *p = reinterpret_cast<const int16_t *>(w.rows + buf * LaneWin<WS>::BUF + w.lane * LaneWin<WS>::ROW) + (mm - base);
-		// The window's samples as a stream of quads fetched TWO quads ahead (a shared-memory load under the fills' traffic
-		// takes longer than four steps); a resampler group ends wherever it ends: a quad that holds a group boundary
-		// takes the per-sample path.  The read-ahead runs at most eleven samples past the lane's last one: inside the
-		// row's slack, the next row, or the slack behind the last buffer (fm_launch adds it) -- never used.
-		int avail = mm < e ? e - mm : 0;
-		Raw q0 = de.fetch(p), q1 = de.fetch(p + 1), q2 = de.fetch(p + 2), q3 = de.fetch(p + 3);
-		Raw q4 = de.fetch(p + 4), q5 = de.fetch(p + 5), q6 = de.fetch(p + 6), q7 = de.fetch(p + 7);
-		while (avail >= 4) {
-			const Raw n0 = de.fetch(p + 8), n1 = de.fetch(p + 9), n2 = de.fetch(p + 10), n3 = de.fetch(p + 11);
-			if (g_left > 4) {
-				a = de.step(a, de.conv(q0)); acc += de.value(a);
-				a = de.step(a, de.conv(q1)); acc += de.value(a);
-				a = de.step(a, de.conv(q2)); acc += de.value(a);
-				a = de.step(a, de.conv(q3)); acc += de.value(a);
-				g_left -= 4;
-			} else {
-				a = de.step(a, de.conv(q0)); acc += de.value(a); if (--g_left == 0) { emit(); }
-				a = de.step(a, de.conv(q1)); acc += de.value(a); if (--g_left == 0) { emit(); }
-				a = de.step(a, de.conv(q2)); acc += de.value(a); if (--g_left == 0) { emit(); }
-				a = de.step(a, de.conv(q3)); acc += de.value(a); if (--g_left == 0) { emit(); }
+		// run by run: what is left of the group in progress, or of the window (a stream of quads fetched two ahead with a
+		// per-sample path for the quads that hold a group boundary measured slower, session AA)
+		while (mm < e) {
+			int run = e - mm;
+			if (run > g_left) { run = g_left; }
+			int j = 0;
+			// up to the next multiple of 4 samples (rows and bases are 8-byte aligned: the position in the row has mm's low bits)
+			for (; ((mm + j) & 3) != 0 && j < run; j++) {
+				const Smp x = de.load(p++);
+				a = de.step(a, x); acc += de.value(a);
 			}
-			q0 = q4; q1 = q5; q2 = q6; q3 = q7; q4 = n0; q5 = n1; q6 = n2; q7 = n3;
-			p += 4; avail -= 4;
+			if (j + 4 <= run) {                    // quads, one 8-byte load each, the next quad fetched ahead (see back_replay)
+				Smp x0, x1, x2, x3;
+				de.load4(p, x0, x1, x2, x3);
+#pragma unroll 2
+				for (; j + 4 <= run; j += 4) {
+					const int16_t *pn = p + 4;             // past the run's end at most into the row's slack
+					Smp y0, y1, y2, y3;
+					de.load4(pn, y0, y1, y2, y3);
+					a = de.step(a, x0); acc += de.value(a);
+					a = de.step(a, x1); acc += de.value(a);
+					a = de.step(a, x2); acc += de.value(a);
+					a = de.step(a, x3); acc += de.value(a);
+					x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+					p += 4;
+				}
+			}
+			for (; j < run; j++) {
+				const Smp x = de.load(p++);
+				a = de.step(a, x); acc += de.value(a);
+			}
+			mm += run; g_left -= run;
+			if (g_left == 0) { emit(); }
 		}
-		if (avail > 0) { a = de.step(a, de.conv(q0)); acc += de.value(a); if (--g_left == 0) { emit(); } }
-		if (avail > 1) { a = de.step(a, de.conv(q1)); acc += de.value(a); if (--g_left == 0) { emit(); } }
-		if (avail > 2) { a = de.step(a, de.conv(q2)); acc += de.value(a); if (--g_left == 0) { emit(); } }
-		if (mm < e) { mm = e; }
 		__syncwarp();
 		if (!more) { break; }
 		base = m_next & ~WIN_ALIGN; buf ^= 1;

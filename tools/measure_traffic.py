@@ -15,13 +15,14 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KERNEL = {"fm2b": "fm_", "fm2a": "fm_", "fm1": "fm_", "fm5a": "fm_", "power3": "power_fft", "power4": "power_fft"}
+LAUNCHES = {"fm2a": 2}          # kernels per step (the stream path: front kernel + back kernel); their traffic is summed
 
 
 def main():
     todo = sys.argv[1:] or list(KERNEL)
     for w in todo:
         cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{KERNEL[w]}",
-               "-c", "2", "--csv", sys.executable, os.path.join(ROOT, "bench.py"), "--workload", w, "--steps", "1", "--warmup", "1",
+               "-c", str(2 * LAUNCHES.get(w, 1)), "--csv", sys.executable, os.path.join(ROOT, "bench.py"), "--workload", w, "--steps", "1", "--warmup", "1",
                "--no-e2e", "--no-cpu", "--no-extras"]
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
         lines = [l for l in out.splitlines() if l.startswith('"')]
@@ -35,10 +36,13 @@ def main():
         if not by_id:
             print(w, "no ncu rows", file=sys.stderr)
             continue
-        last = by_id[sorted(by_id, key=int)[-1]]                  # the second launch: caches warm like a timed step
-        total = last.get("dram__bytes_read.sum", 0.0) + last.get("dram__bytes_write.sum", 0.0)
+        ids = sorted(by_id, key=int)[-LAUNCHES.get(w, 1):]        # the second step's launches: caches warm like a timed step
+        rd = sum(by_id[i].get("dram__bytes_read.sum", 0.0) for i in ids)
+        wr = sum(by_id[i].get("dram__bytes_write.sum", 0.0) for i in ids)
+        total = rd + wr
+        last = {"kernel": " + ".join(by_id[i]["kernel"] for i in ids)}
         rec = {"workload": w, "kernel": last["kernel"], "dram_bytes_per_launch": total,
-               "dram_bytes_read": last.get("dram__bytes_read.sum"), "dram_bytes_write": last.get("dram__bytes_write.sum"),
+               "dram_bytes_read": rd, "dram_bytes_write": wr,
                "source_sha16": bench.kernel_source_sha(w),
                "from": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, second launch of bench.py --steps 1 --warmup 1"}
         with open(os.path.join(ROOT, "profiles", f"traffic_{w}.json"), "w") as f:

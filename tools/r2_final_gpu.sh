@@ -3,7 +3,7 @@
 # (default workload with the extras and the CPU baseline), one bench line per workload, the reference arm, DRAM traffic
 # per workload, the ncu pages (raw + source CSV) of the fm2b and power3 kernels and the launch list of the bench command.
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/r2final; mkdir -p $OUT
+OUT=gpurun_out/r2final2; mkdir -p $OUT
 exec > >(tee $OUT/session.log) 2>&1
 date; nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv
 T0=$SECONDS
@@ -18,7 +18,7 @@ RXB200_FM_NOROWS=1 timeout 200 python bench.py --no-extras --no-cpu --no-e2e > $
 timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "reference rc=$? t=$((SECONDS-T0))"
 python - <<'PY'
 import json, glob, os
-for f in sorted(glob.glob("gpurun_out/r2final/bench_*.json")):
+for f in sorted(glob.glob("gpurun_out/r2final2/bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         r = d.get("roofline") or {}
@@ -33,6 +33,11 @@ for w in fm2b power3; do
 	ncu -i /tmp/prof_$w.ncu-rep --page raw --csv > $OUT/raw_$w.csv 2>/dev/null
 	ncu -i /tmp/prof_$w.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip > $OUT/src_$w.csv.gz
 done
+# the stream path's two kernels on fm2a (second step's launches)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fm_ -s 2 -c 2 -o /tmp/prof_fm2a -f \
+	python bench.py --workload fm2a --steps 1 --warmup 1 --no-e2e --no-cpu --no-extras > $OUT/ncu_full_fm2a.log 2>&1; echo "ncu fm2a rc=$? t=$((SECONDS-T0))"
+ncu -i /tmp/prof_fm2a.ncu-rep --page raw --csv > $OUT/raw_fm2a.csv 2>/dev/null
+(cd tools/experiments && timeout 120 ./op_microbench.bin) > $OUT/op_microbench.txt 2>&1; echo "microbench rc=$?"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_bench.csv \
 	python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$? t=$((SECONDS-T0))"
 date
