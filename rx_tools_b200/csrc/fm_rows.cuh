@@ -176,26 +176,58 @@ __device__ __forceinline__ uint32_t row_body(const FmDev &c, uint32_t *xs, int p
 	if (lane == 31) { xs[RS::FPRE + par] = last; }
 	if (lane == 0) { prev = xs[RS::FPRE + (par ^ 1)]; }
 	int br = lo16(prev), bj = hi16(prev);
-	int pcm[NV];
+	int cr[NV], cj[NV];
 #pragma unroll
 	for (int j = 0; j < NV; j++) {
-		const int cr = add_w(mul_w(di[j], br), mul_w(dq[j], bj));
-		const int cj = sub_w(mul_w(dq[j], br), mul_w(di[j], bj));
-		pcm[j] = fast_atan2_i(cj, cr);
-		if (CS && j == 0 && lane == 0) { pcm[0] = disc_std(cr, cj); }       // F8: the first sample of a chunk goes through atan2
+		cr[j] = add_w(mul_w(di[j], br), mul_w(dq[j], bj));
+		cj[j] = sub_w(mul_w(dq[j], br), mul_w(di[j], bj));
 		br = di[j]; bj = dq[j];
 	}
+	// fast_atan2 in FP32 (fast_atan2_f32: every quantity an integer a float holds exactly).  Its operands always fit: the
+	// chain from the 8-bit-range samples to here is linear with non-negative half-band taps, so |d| <= 128 * sum|g| with g
+	// the combined response of the P passes and the droop FIR -- 405 / 835 / 1684 for P = 1 / 2 / 3 (1024 without the FIR),
+	// plus less than 32 for the floors -- and |cr| + |cj| <= 4 d^2 < 1.2e7 < 2^24
+	// (tests/test_host_logic.py::test_row_discriminator_operands_fit_fp32 recomputes the bound from the table).
+	// The FP32 form issues every cycle and leaves the adder pipe, which bounds this loop, ~16 instructions per output
+	// lighter: 681 -> 705 Gsamples/s on fm2b (session AD).  ROWS_DISC_F32 0: the integer form.
+#ifndef ROWS_DISC_F32
+#define ROWS_DISC_F32 1
+#endif
+	uint32_t wpk[NV / 2];                  // PCM, two samples per word
+#if ROWS_DISC_F32
+	{
+		uint32_t ab[NV];
+#pragma unroll
+		for (int j = 0; j < NV; j++) {
+			float ang = fast_atan2_f32(__int2float_rn(cj[j]), __int2float_rn(cr[j]));
+			if (CS && j == 0 && lane == 0) { ang = __int2float_rn(disc_std(cr[0], cj[0])); }   // F8: the first sample of a chunk goes through atan2
+			ab[j] = (uint32_t)__float_as_int(__fadd_rn(ang, 12582912.0f));      // low 16 bits of angle + 1.5 * 2^23: the int16 value
+		}
+#pragma unroll
+		for (int j = 0; j < NV; j += 2) { wpk[j / 2] = __byte_perm(ab[j], ab[j + 1], 0x5410); }
+	}
+#else
+	{
+		int pcm[NV];
+#pragma unroll
+		for (int j = 0; j < NV; j++) {
+			pcm[j] = fast_atan2_i(cj[j], cr[j]);
+			if (CS && j == 0 && lane == 0) { pcm[0] = disc_std(cr[0], cj[0]); }
+		}
+#pragma unroll
+		for (int j = 0; j < NV; j += 2) { wpk[j / 2] = ((uint32_t)pcm[j] & 0xffffu) | ((uint32_t)pcm[j + 1] << 16); }
+	}
+#endif
 	if (store) {
 		int16_t *dst = pcm_s + pcm_phys<PCM_PAD_ROWS>(rel);
 #pragma unroll
 		for (int j = 0; j < NV; j += 4) {
 			uint2 w;
-			w.x = ((uint32_t)pcm[j] & 0xffffu) | ((uint32_t)pcm[j + 1] << 16);
-			w.y = ((uint32_t)pcm[j + 2] & 0xffffu) | ((uint32_t)pcm[j + 3] << 16);
+			w.x = wpk[j / 2]; w.y = wpk[j / 2 + 1];
 			*reinterpret_cast<uint2 *>(dst + j) = w;
 		}
 	}
-	return (uint32_t)pcm[NV - 1];
+	return wpk[NV / 2 - 1];
 }
 
 // The rows [r0, r1) of one work item that this warp owns (rows are counted from the start of the channel's call).

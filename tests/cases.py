@@ -51,6 +51,18 @@ def fm_cases(scale: int = 1) -> list[FmCase]:
     cs.append(FmCase("cfg2B_chunk65536", FmParams(downsample=8, downsample_passes=3, comp_fir_size=9,
                                                   custom_atan=ATAN_FAST, deemph=1, deemph_a=23, rate_out=300_000,
                                                   rate_out2=48_000), _wb(n), 65536))
+    # a full-scale tone that lands on the decimated Nyquist frequency after the fs/4 rotation (-fs/4 + fs/16), where the droop
+    # FIR has its largest gain (4.4) and consecutive decimated samples alternate in sign: the largest conjugate products a
+    # tone can give the row front end's FP32 discriminator (fm_rows.cuh); second half ordinary signal
+    def _overshoot():
+        k = np.arange(n // 2)
+        ph = 2.0 * np.pi * (-3.0 / 16.0) * k
+        x = np.empty(n, dtype=np.int16)              # n // 2 complex samples of the tone
+        x[0::2] = np.clip(np.round(32767 * np.cos(ph)), -32768, 32767).astype(np.int16)
+        x[1::2] = np.clip(np.round(32767 * np.sin(ph)), -32768, 32767).astype(np.int16)
+        return np.concatenate([x, _wb(n // 2, seed=61)()])
+    cs.append(FmCase("cfg2B_fir_overshoot", FmParams(downsample=8, downsample_passes=3, comp_fir_size=9, custom_atan=ATAN_FAST,
+                                                     deemph=1, deemph_a=23, rate_out=300_000, rate_out2=48_000), _overshoot, C))
     # wbfm with one and two passes + droop FIR (-s 1200k / -s 600k -F 9): the row front end's P = 1, 2 instantiations
     cs.append(FmCase("wbfm_P1_fir", FmParams(downsample=2, downsample_passes=1, comp_fir_size=9, custom_atan=ATAN_FAST,
                                              deemph=1, deemph_a=91, rate_out=1_200_000, rate_out2=48_000), _wb(n, seed=41), C))

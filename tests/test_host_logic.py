@@ -138,3 +138,33 @@ def test_fast_atan2_fp32_form():
     want = _fast_atan2_ref(y, x)
     for shift in (-1, 0, 1):
         assert np.array_equal(_fast_atan2_f32(y, x, shift), want), shift
+
+
+def test_row_discriminator_operands_fit_fp32():
+    """The row front end (csrc/fm_rows.cuh) runs fast_atan2 in FP32 without a range check: its operands must stay below 2^24.
+    The chain from the 8-bit-range samples (|x| <= 128, src/rtl_fm.c:846) to the discriminator is linear with non-negative
+    half-band taps (fifth_order, :411-440) followed by the droop FIR (generic_fir, :442-465; the product's copy of
+    cic_9_tables is read from csrc/fm_kernels.cu), so |d| <= 128 * sum|g| for the combined response g, plus the floors'
+    slack; the conjugate product's components obey |cr| + |cj| <= (|di| + |dq|)(|bi| + |bq|) <= 4 d^2."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "rx_tools_b200", "csrc", "fm_kernels.cu")).read()
+    body = re.search(r"k_droop9_host\[11\]\[10\] = \{(.*?)\n\};", src, re.S).group(1)
+    table = [[int(v) for v in row.split(",") if v.strip()] for row in re.findall(r"\{(\s*-?\d+\s*(?:,\s*-?\d+\s*)*)\}", body)]
+    b = np.array([1, 5, 10, 10, 5, 1], dtype=np.float64) / 16.0
+
+    def up(v, k):
+        o = np.zeros((len(v) - 1) * k + 1)
+        o[::k] = v
+        return o
+
+    for P in (1, 2, 3):                                    # the row front end's instantiations
+        h = np.array([1.0])
+        for lvl in range(P):
+            h = np.convolve(h, up(b, 2 ** lvl))
+        assert abs(128 * np.abs(h).sum() - 128 * 2 ** P) < 1e-9          # without the FIR: |d| <= 128 << P
+        c = np.array(table[P][1:10], dtype=np.float64) / 32768.0
+        assert table[P][0] == 9 and np.array_equal(c, c[::-1])
+        g = np.convolve(up(c, 2 ** P), h)
+        floors = sum(2 ** (P - 1 - lvl) for lvl in range(P)) * np.abs(c).sum() + 1      # one unit per floor, amplified downstream
+        dmax = 128 * np.abs(g).sum() + floors
+        assert 4 * dmax * dmax < 2 ** 24, (P, dmax)

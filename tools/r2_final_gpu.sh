@@ -3,7 +3,7 @@
 # (default workload with the extras and the CPU baseline), one bench line per workload, the reference arm, DRAM traffic
 # per workload, the ncu pages (raw + source CSV) of the fm2b and power3 kernels and the launch list of the bench command.
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/r2final2; mkdir -p $OUT
+OUT=gpurun_out/r2final3; mkdir -p $OUT
 exec > >(tee $OUT/session.log) 2>&1
 date; nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv
 T0=$SECONDS
@@ -18,7 +18,7 @@ RXB200_FM_NOROWS=1 timeout 200 python bench.py --no-extras --no-cpu --no-e2e > $
 timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "reference rc=$? t=$((SECONDS-T0))"
 python - <<'PY'
 import json, glob, os
-for f in sorted(glob.glob("gpurun_out/r2final2/bench_*.json")):
+for f in sorted(glob.glob("gpurun_out/r2final3/bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         r = d.get("roofline") or {}
