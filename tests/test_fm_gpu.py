@@ -118,6 +118,25 @@ def test_fm_multichannel(port):
     d.close()
 
 
+@pytest.mark.parametrize("name,stream", [("cfg2A", True), ("cfg2B", False)])
+def test_wbfm_multichannel(name, stream, port, monkeypatch):
+    """Several channels through the wbfm kernels: the stream path (front kernel + fm_back_kernel: per-channel PCM scratch,
+    items and look-back chains that must not cross a channel) and the split kernel with the row front end."""
+    case = next(c for c in fm_cases() if c.name == name)
+    if stream:
+        monkeypatch.setenv("RXB200_FM_STREAM_MIN", "0")
+        monkeypatch.setenv("RXB200_FM_STREAM_PIECE", "700")        # several items per channel
+    x = case.make_input()
+    n = (x.size // 3 // case.chunk_int16) * case.chunk_int16 or case.chunk_int16
+    xs = np.stack([x[:n], x[x.size - n:], np.zeros(n, dtype=np.int16)])           # two different signals and silence
+    d = fm.FmDemod(case.params, n_channels=3)
+    got = d.full_demod(xs, case.chunk_int16)
+    assert d.stats()["kernel_kind"] == (3 if stream else 1)
+    for ch in range(3):
+        _compare(case, got[ch], port.fm_run(case.params, xs[ch], case.chunk_int16))
+    d.close()
+
+
 def test_scale_identity_on_gpu(port):
     """All 65536 CS16 values through the scale stage (raw mode, D=1, offset tuning = no rotation)."""
     p = oracle.FmParams(mode=oracle.MODE_RAW, downsample=1, offset_tuning=1, rate_out=1000000)
