@@ -168,3 +168,22 @@ def test_row_discriminator_operands_fit_fp32():
         floors = sum(2 ** (P - 1 - lvl) for lvl in range(P)) * np.abs(c).sum() + 1      # one unit per floor, amplified downstream
         dmax = 128 * np.abs(g).sum() + floors
         assert 4 * dmax * dmax < 2 ** 24, (P, dmax)
+
+
+def test_resampler_group_closed_form():
+    """fm_back_kernel knows where a lane stops before it starts: n outputs of low_pass_real (src/rtl_fm.c:396-407) end with the
+    first sample that takes the running phase to n * fast, i.e. after ceil((n * fast - phase) / slow) samples (win_outputs,
+    csrc/fm_kernels.cu).  Checked against the reference's loop for integer and fractional rate ratios."""
+    rng = np.random.default_rng(3)
+    for fast, slow in [(2_400_000, 48_000), (300_000, 48_000), (170_000, 32_000), (1_024_000, 24_000), (1_200_000, 44_100)]:
+        for _ in range(50):
+            phase = int(rng.integers(0, slow))             # a piece starts right after an emission: phase < slow
+            n = int(rng.integers(1, 200))
+            ph, samples, outs = phase, 0, 0
+            while outs < n:                                # the reference's loop
+                samples += 1
+                ph += slow
+                if ph >= fast:
+                    ph -= fast
+                    outs += 1
+            assert samples == (n * fast - phase + slow - 1) // slow, (fast, slow, phase, n)
