@@ -408,6 +408,51 @@ __device__ __forceinline__ float fast_atan2_f32(float y, float x)
 	return (den == 0.0f) ? 0.0f : r;
 }
 
+// polar_discriminant in FP32 with a guard band (operands below 2^24, i.e. exact in a float: always so without decimation).
+// The fp64 form above costs ~100 instructions, most of them at the fp64 pipe's rate; here the angle is estimated in
+// FP32 -- t = min/max by reciprocal + one exact-remainder step, atan(t) = t + t^3 q(t^2) with a degree-8 q (6.7e-8 rad on
+// [0, 1]), times 16384/3.14159 as a two-float constant -- and assembled as an INTEGER part plus a small FRACTION per octant
+// (8192.0069 - v, 16384.0138 - v: the constants' integer parts in integer arithmetic), so the only error is the
+// estimate's own: 4.1e-4 output units at most over 6 M operand pairs.  Whenever the fraction is within 1.5e-3 of an
+// integer (0.3 % of the samples) the truncation could go either way and the fp64 form decides.  Same results as
+// disc_std_lean; the algorithm restated in numpy and checked against fp64 atan2 (tests/test_host_logic.py::test_polar_disc_fp32_form).
+#ifndef DISC_STD_F32
+#define DISC_STD_F32 1
+#endif
+__device__ __forceinline__ int disc_std_f32(int cr, int cj)
+{
+	if (cj == 0 && cr >= 0) { return 0; }
+	if (!DISC_STD_F32 || (unsigned)cr + (1u << 24) >= (1u << 25) || (unsigned)cj + (1u << 24) >= (1u << 25)) { return disc_std_lean(cr, cj); }
+	const float ax = fabsf(__int2float_rn(cr)), ay = fabsf(__int2float_rn(cj));
+	const float a = fminf(ax, ay), b = fmaxf(ax, ay);                  // b >= 1
+	const float r = rcp_est(b);
+	const float t0 = __fmul_rn(a, r);
+	const float t = __fmaf_rn(__fmaf_rn(-t0, b, a), r, t0);            // a / b to half an ulp
+	const float u = __fmul_rn(t, t);
+	float q = -0.002447017002850771f;
+	q = __fmaf_rn(q, u, 0.013750223442912102f);
+	q = __fmaf_rn(q, u, -0.03627006709575653f);
+	q = __fmaf_rn(q, u, 0.06284350901842117f);
+	q = __fmaf_rn(q, u, -0.08673165738582611f);
+	q = __fmaf_rn(q, u, 0.11037992686033249f);
+	q = __fmaf_rn(q, u, -0.14279110729694366f);
+	q = __fmaf_rn(q, u, 0.1999976634979248f);
+	q = __fmaf_rn(q, u, -0.3333333134651184f);
+	const float p = __fmaf_rn(__fmul_rn(t, u), q, t);                  // atan(t), 0 <= t <= 1
+	const float KHI = 5215.193359375f, KLO = 0.00022094578889664263f;  // 16384 / 3.14159 in two floats
+	const float nm = __fadd_rd(__fmul_rn(p, KHI), 12582912.0f);        // 1.5 * 2^23 + floor(p * KHI)
+	const float n1 = __fsub_rn(nm, 12582912.0f);
+	float F = __fmaf_rn(p, KLO, __fmaf_rn(p, KHI, -n1));               // the fraction, in [-eps, 1 + eps)
+	int N = __float_as_int(nm) - 0x4B400000;                           // the integer part
+	if (ay > ax) { N = 8191 - N; F = __fsub_rn(1.0069195032119751f, F); }       // pi/2 - angle: 8192.00692 - v
+	if (cr < 0) { N = 16383 - N; F = __fsub_rn(1.0138390064239502f, F); }       // pi - angle: 16384.01384 - v
+	const float Fm = __fadd_rn(F, 12582912.0f);                        // 1.5 * 2^23 + rint(F)
+	const float Fr = __fsub_rn(Fm, 12582912.0f);
+	if (fabsf(__fsub_rn(F, Fr)) < 1.5e-3f) { return disc_std_lean(cr, cj); }
+	const int k = N + (__float_as_int(Fm) - 0x4B400000) - (F < Fr ? 1 : 0);    // N + floor(F)
+	return cj < 0 ? -k : k;
+}
+
 // polar_disc_lut (src/rtl_fm.c:528-564)
 __device__ __forceinline__ int disc_lut(const int *__restrict__ lut, int cr, int cj)
 {
@@ -533,7 +578,7 @@ __device__ __forceinline__ void post_decim(const FmDev &c, const FmCall &k, Fron
 		int br = s.pre_i, bj = s.pre_q;
 		int cr = add_w(mul_w(di, br), mul_w(dq, bj));       // x[n] * conj(x[n-1]) (src/rtl_fm.c:470-474)
 		int cj = sub_w(mul_w(dq, br), mul_w(di, bj));
-		if (am == RXB200_ATAN_STD) { pcm = disc_std_lean(cr, cj); }
+		if (am == RXB200_ATAN_STD) { pcm = disc_std_f32(cr, cj); }
 		else if (e.first_in_chunk) { pcm = disc_std(cr, cj); }                     // F8: one sample per chunk, out of line
 		else if (am == RXB200_ATAN_FAST) { pcm = fast_atan2_i(cj, cr); }
 		else if (am == RXB200_ATAN_LUT) { pcm = disc_lut(c.atan_lut, cr, cj); }

@@ -187,3 +187,68 @@ def test_resampler_group_closed_form():
                     ph -= fast
                     outs += 1
             assert samples == (n * fast - phase + slow - 1) // slow, (fast, slow, phase, n)
+
+
+def test_polar_disc_fp32_form():
+    """polar_discriminant (src/rtl_fm.c:476-483: (int)(atan2(cj, cr) / 3.14159 * 2^14)) as the CUDA path evaluates it for operands
+    that are exact in a float (disc_std_f32, csrc/fm_kernels.cu): an FP32 estimate assembled as integer part + fraction, and a
+    guard band inside which the fp64 form decides.  Restated here step for step in numpy float32 (constants copied from the
+    kernel); outside the guard band the result must equal the fp64 truncation for every operand pair, whatever the reciprocal
+    estimate's last bit, and the guard band must stay a small fraction of the samples."""
+    f = np.float32
+    q_coef = [f(c) for c in (-0.3333333134651184, 0.1999976634979248, -0.14279110729694366, 0.11037992686033249,
+                             -0.08673165738582611, 0.06284350901842117, -0.03627006709575653, 0.013750223442912102,
+                             -0.002447017002850771)]
+    khi, klo = f(5215.193359375), f(0.00022094578889664263)
+    one_c2, one_c4, delta = f(1.0069195032119751), f(1.0138390064239502), f(1.5e-3)
+    src = open(os.path.join(os.path.dirname(__file__), "..", "rx_tools_b200", "csrc", "fm_kernels.cu")).read()
+    for lit in ("-0.002447017002850771f", "5215.193359375f", "0.00022094578889664263f", "1.0069195032119751f",
+                "1.0138390064239502f", "1.5e-3f", "0.1999976634979248f"):
+        assert lit in src, lit                         # the kernel still uses these constants
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.float64(b) + np.float64(c)).astype(f) if np.isscalar(b) or np.ndim(b) == 0 else \
+            (a.astype(np.float64) * b.astype(np.float64) + (c.astype(np.float64) if np.ndim(c) else np.float64(c))).astype(f)
+
+    def form(y, x, ulp):
+        ax, ay = np.abs(x.astype(f)), np.abs(y.astype(f))
+        a, b = np.minimum(ax, ay), np.maximum(ax, ay)
+        r = (f(1) / b).astype(f)
+        r = (r.view(np.int32) + ulp).view(f)
+        t0 = (a * r).astype(f)
+        t = fma(fma(-t0, b, a), r, t0)
+        u = (t * t).astype(f)
+        q = np.full_like(u, q_coef[-1])
+        for c in q_coef[-2::-1]:
+            q = fma(q, u, np.full_like(u, c))
+        p = fma((t * u).astype(f), q, t)
+        n1 = np.floor((p * khi).astype(f)).astype(f)
+        fr = fma(p, np.full_like(p, klo), fma(p, np.full_like(p, khi), -n1))
+        n = n1.astype(np.int64)
+        swap, neg = ay > ax, x < 0
+        n = np.where(swap, 8191 - n, n)
+        fr = np.where(swap, (one_c2 - fr).astype(f), fr)
+        n = np.where(neg, 16383 - n, n)
+        fr = np.where(neg, (one_c4 - fr).astype(f), fr)
+        rr = np.rint(fr)
+        sure = np.abs(fr - rr) >= delta
+        k = n + rr.astype(np.int64) - (fr < rr)
+        return np.where(y < 0, -k, k), sure
+
+    rng = np.random.default_rng(5)
+    g = np.arange(-150, 151, dtype=np.int64)
+    sets = [(np.repeat(g, g.size), np.tile(g, g.size)),
+            (rng.integers(-32768, 32769, 3_000_000), rng.integers(-32768, 32769, 3_000_000)),
+            (rng.integers(-300, 301, 1_000_000), rng.integers(-32768, 32769, 1_000_000)),
+            (rng.integers(-(1 << 24) + 1, 1 << 24, 1_000_000), rng.integers(-(1 << 24) + 1, 1 << 24, 1_000_000))]
+    total = unsure = 0
+    for y, x in sets:
+        keep = ~((y == 0) & (x >= 0))                  # the kernel returns 0 for these before anything else
+        y, x = y[keep], x[keep]
+        want = np.trunc(np.arctan2(y.astype(np.float64), x.astype(np.float64)) / 3.14159 * 16384).astype(np.int64)
+        for ulp in (-1, 0, 1):
+            k, sure = form(y, x, ulp)
+            assert np.array_equal(k[sure], want[sure]), ulp
+            total += y.size
+            unsure += int((~sure).sum())
+    assert unsure < 0.006 * total
